@@ -1,0 +1,879 @@
+// cybayes_b200 -- host scheduler and C ABI (see include/cybayes_b200.h).
+//
+// One context drives one B200: leaf state codes, a pool of P matrices and a pool of
+// partial-likelihood buffers live in HBM; an evaluation is turned into a handful of kernel
+// launches (one per tree level, or ONE for a dirty path / a batch of candidate paths) on a
+// single stream, followed by an optional scalar NCCL all-reduce and an 8-byte read-back.
+// Snapshots are immutable node -> buffer tables with reference-counted buffers: the
+// copy-on-write equivalent of the reference's aliased cache dicts (ML_gamma.pyx:114).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <limits.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "cb_types.cuh"
+#include "kernels_general.cuh"
+#include "kernels_pmat.cuh"
+#include "kernels_s2.cuh"
+
+using namespace cb;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define REQUIRE(cond, ...)            \
+  do {                                \
+    if (!(cond)) return fail(__VA_ARGS__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------- NCCL (dlopen)
+struct NcclId { char internal[128]; };
+typedef struct ncclComm* ncclComm_t;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+  if (g_nccl.lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  REQUIRE(g_nccl.lib, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, NcclId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy,
+          "libnccl is missing expected symbols");
+  return 0;
+}
+enum { NCCL_DOUBLE = 8, NCCL_SUM = 0 };  // ncclFloat64 / ncclSum in nccl.h
+
+// ------------------------------------------------------------------------------ context
+struct Buffer {
+  double* data = nullptr;
+  int32_t* scale = nullptr;
+  int refs = 0;
+};
+struct Snapshot {
+  std::vector<int32_t> buf_of_node;  // index by node id; -1 = absent
+  int refs = 0;
+};
+
+struct cb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
+  int sm_count = 148;
+  // alignment
+  int n_taxa = 0, n_states = 0, n_cats = 0, code_bytes = 1, n_amb = 0;
+  int64_t n_sites = 0, P = 0;  // real and padded pattern counts
+  bool family_s2 = false;
+  void* d_codes = nullptr;
+  double* d_weights = nullptr;
+  double* d_amb = nullptr;
+  double* d_pi = nullptr;
+  // P matrices
+  double* d_pmats = nullptr;
+  int pmat_cap = 0;
+  // partial buffers
+  std::vector<Buffer> buffers;
+  std::vector<int> free_buffers;
+  size_t buffer_bytes = 0;
+  std::vector<Snapshot> snaps;
+  std::vector<int> free_snaps;
+  // staging
+  OpDesc* h_ops = nullptr;
+  OpDesc* d_ops = nullptr;
+  int ops_cap = 0;
+  RangeDesc* h_ranges = nullptr;
+  RangeDesc* d_ranges = nullptr;
+  int ranges_cap = 0;
+  double* d_block_sums = nullptr;
+  unsigned* d_tickets = nullptr;
+  double* d_results = nullptr;
+  double* h_results = nullptr;
+  double* d_root_dot = nullptr;
+  int32_t* d_root_exp = nullptr;
+  int out_cap = 0, max_blocks = 0;
+  int last_n_out = 0;
+  // scratch for pmat builds
+  void* d_scratch = nullptr;
+  void* h_scratch = nullptr;
+  size_t scratch_cap = 0;
+  // L2 flush
+  void* d_flush = nullptr;
+  size_t flush_bytes = 0;
+  // NCCL
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1;
+  // work vectors reused across evals
+  std::vector<int32_t> op_of_node, level_of_op, order;
+  // stats
+  int64_t launches = 0, h2d = 0, d2h = 0, dev_bytes = 0;
+  bool timing_valid = false;
+};
+
+static int dev_alloc(cb_ctx* c, void** p, size_t bytes) {
+  CU(cudaMalloc(p, bytes));
+  c->dev_bytes += (int64_t)bytes;
+  return 0;
+}
+static void dev_free(cb_ctx* c, void* p, size_t bytes) {
+  if (p) {
+    cudaFree(p);
+    c->dev_bytes -= (int64_t)bytes;
+  }
+}
+
+extern "C" const char* cb_last_error(void) { return g_err.c_str(); }
+extern "C" int cb_version(void) { return 100; }
+extern "C" int cb_device_count(int* out) {
+  REQUIRE(out, "null argument");
+  CU(cudaGetDeviceCount(out));
+  return 0;
+}
+
+extern "C" int cb_create(int device, cb_ctx** out) {
+  REQUIRE(out, "null argument");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail("no CUDA device available (%s); cybayes_b200 has no CPU fallback", cudaGetErrorString(e));
+  REQUIRE(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+  CU(cudaSetDevice(device));
+  cb_ctx* c = new cb_ctx();
+  c->device = device;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  CU(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CU(cudaFuncSetAttribute(prune_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  *out = c;
+  return 0;
+}
+
+static void free_alignment(cb_ctx* c) {
+  for (auto& b : c->buffers) dev_free(c, b.data, c->buffer_bytes);
+  c->buffers.clear();
+  c->free_buffers.clear();
+  c->snaps.clear();
+  c->free_snaps.clear();
+  if (c->d_codes) dev_free(c, c->d_codes, (size_t)c->n_taxa * c->P * c->code_bytes);
+  if (c->d_weights) dev_free(c, c->d_weights, (size_t)c->P * 8);
+  if (c->d_amb) dev_free(c, c->d_amb, (size_t)std::max(1, c->n_amb) * c->n_states * 8);
+  if (c->d_pi) dev_free(c, c->d_pi, (size_t)c->n_states * 8);
+  if (c->d_pmats) dev_free(c, c->d_pmats, (size_t)c->pmat_cap * c->n_states * c->n_states * 8);
+  c->d_codes = nullptr;
+  c->d_weights = c->d_amb = c->d_pi = c->d_pmats = nullptr;
+  c->pmat_cap = 0;
+  if (c->d_block_sums) dev_free(c, c->d_block_sums, (size_t)c->out_cap * c->max_blocks * 8);
+  if (c->d_tickets) dev_free(c, c->d_tickets, (size_t)c->out_cap * 4);
+  if (c->d_results) dev_free(c, c->d_results, (size_t)c->out_cap * 8);
+  if (c->d_root_dot) dev_free(c, c->d_root_dot, (size_t)c->out_cap * c->n_cats * c->P * 8);
+  if (c->d_root_exp) dev_free(c, c->d_root_exp, (size_t)c->out_cap * c->n_cats * c->P * 4);
+  if (c->h_results) cudaFreeHost(c->h_results);
+  c->d_block_sums = c->d_results = c->d_root_dot = nullptr;
+  c->d_tickets = nullptr;
+  c->d_root_exp = nullptr;
+  c->h_results = nullptr;
+  c->out_cap = 0;
+}
+
+extern "C" int cb_destroy(cb_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  free_alignment(c);
+  if (c->d_ops) dev_free(c, c->d_ops, (size_t)c->ops_cap * sizeof(OpDesc));
+  if (c->d_ranges) dev_free(c, c->d_ranges, (size_t)c->ranges_cap * sizeof(RangeDesc));
+  if (c->h_ops) cudaFreeHost(c->h_ops);
+  if (c->h_ranges) cudaFreeHost(c->h_ranges);
+  if (c->d_scratch) dev_free(c, c->d_scratch, c->scratch_cap);
+  if (c->h_scratch) cudaFreeHost(c->h_scratch);
+  if (c->d_flush) dev_free(c, c->d_flush, c->flush_bytes);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev_stage);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+// --------------------------------------------------------------------------------- NCCL
+extern "C" int cb_nccl_unique_id(void* id128_out) {
+  REQUIRE(id128_out, "null argument");
+  if (load_nccl()) return 1;
+  NcclId id;
+  int r = g_nccl.GetUniqueId(&id);
+  REQUIRE(r == 0, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  memcpy(id128_out, &id, sizeof id);
+  return 0;
+}
+extern "C" int cb_comm_init(cb_ctx* c, const void* id128, int rank, int n_ranks) {
+  REQUIRE(c && id128, "null argument");
+  REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad rank %d of %d", rank, n_ranks);
+  if (load_nccl()) return 1;
+  CU(cudaSetDevice(c->device));
+  NcclId id;
+  memcpy(&id, id128, sizeof id);
+  int r = g_nccl.CommInitRank(&c->comm, n_ranks, id, rank);
+  REQUIRE(r == 0, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  c->n_ranks = n_ranks;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- alignment
+static int ensure_scratch(cb_ctx* c, size_t bytes) {
+  if (bytes <= c->scratch_cap) return 0;
+  size_t cap = std::max(bytes, c->scratch_cap * 2);
+  cap = (cap + 4095) & ~(size_t)4095;
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->d_scratch) dev_free(c, c->d_scratch, c->scratch_cap);
+  if (c->h_scratch) cudaFreeHost(c->h_scratch);
+  c->d_scratch = c->h_scratch = nullptr;
+  c->scratch_cap = 0;
+  if (dev_alloc(c, &c->d_scratch, cap)) return 1;
+  CU(cudaMallocHost(&c->h_scratch, cap));
+  c->scratch_cap = cap;
+  return 0;
+}
+
+extern "C" int cb_set_tips(cb_ctx* c, int n_taxa, int64_t n_sites, int n_states, int n_cats,
+                           const void* codes, int code_bytes, const double* amb_sets, int n_amb,
+                           const double* weights) {
+  REQUIRE(c && codes, "null argument");
+  REQUIRE(n_taxa >= 2 && n_sites >= 1 && n_states >= 2, "bad alignment shape %d x %lld x %d", n_taxa,
+          (long long)n_sites, n_states);
+  REQUIRE(n_cats >= 1 && n_cats <= CB_MAX_CATS, "n_cats must be 1..%d", CB_MAX_CATS);
+  REQUIRE(code_bytes == 1 || code_bytes == 2, "code_bytes must be 1 or 2");
+  REQUIRE(n_amb >= 1 && amb_sets, "amb_sets must at least hold the all-ones set");
+  REQUIRE(n_states + n_amb <= (code_bytes == 1 ? 256 : 65536), "codes do not fit code_bytes");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  free_alignment(c);
+  c->n_taxa = n_taxa;
+  c->n_sites = n_sites;
+  c->n_states = n_states;
+  c->n_cats = n_cats;
+  c->code_bytes = code_bytes;
+  c->n_amb = n_amb;
+  c->P = (n_sites + 63) / 64 * 64;
+  c->family_s2 = (n_states == 2 && (n_cats == 4 || n_cats == 1));
+  const int64_t P = c->P;
+  if (dev_alloc(c, &c->d_codes, (size_t)n_taxa * P * code_bytes)) return 1;
+  // padding sites carry the all-ones code (a no-op factor) and weight 0
+  if (code_bytes == 1) {
+    CU(cudaMemsetAsync(c->d_codes, n_states, (size_t)n_taxa * P, c->stream));
+  } else {
+    std::vector<uint16_t> fill((size_t)P, (uint16_t)n_states);
+    for (int t = 0; t < n_taxa; ++t)
+      CU(cudaMemcpyAsync((char*)c->d_codes + (size_t)t * P * 2, fill.data(), (size_t)P * 2, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  CU(cudaMemcpy2DAsync(c->d_codes, (size_t)P * code_bytes, codes, (size_t)n_sites * code_bytes,
+                       (size_t)n_sites * code_bytes, n_taxa, cudaMemcpyHostToDevice, c->stream));
+  c->h2d += (int64_t)n_taxa * n_sites * code_bytes;
+  if (dev_alloc(c, (void**)&c->d_weights, (size_t)P * 8)) return 1;
+  CU(cudaMemsetAsync(c->d_weights, 0, (size_t)P * 8, c->stream));
+  {
+    std::vector<double> w((size_t)n_sites, 1.0);
+    if (weights) memcpy(w.data(), weights, (size_t)n_sites * 8);
+    CU(cudaMemcpyAsync(c->d_weights, w.data(), (size_t)n_sites * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->h2d += n_sites * 8;
+  }
+  if (dev_alloc(c, (void**)&c->d_amb, (size_t)n_amb * n_states * 8)) return 1;
+  CU(cudaMemcpyAsync(c->d_amb, amb_sets, (size_t)n_amb * n_states * 8, cudaMemcpyHostToDevice, c->stream));
+  if (dev_alloc(c, (void**)&c->d_pi, (size_t)n_states * 8)) return 1;
+  CU(cudaStreamSynchronize(c->stream));
+  const size_t scale_ints = c->family_s2 ? (size_t)P : (size_t)n_cats * P;
+  c->buffer_bytes = (size_t)n_cats * n_states * P * 8 + scale_ints * 4;
+  return 0;
+}
+
+// ------------------------------------------------------------------------ P matrices
+extern "C" int cb_pmat_reserve(cb_ctx* c, int n_slots) {
+  REQUIRE(c && c->n_states > 0, "cb_set_tips must come first");
+  if (n_slots <= c->pmat_cap) return 0;
+  CU(cudaSetDevice(c->device));
+  int cap = std::max(n_slots, std::max(1024, c->pmat_cap * 2));
+  const size_t mat = (size_t)c->n_states * c->n_states * 8;
+  double* nd = nullptr;
+  if (dev_alloc(c, (void**)&nd, (size_t)cap * mat)) return 1;
+  if (c->d_pmats) {
+    CU(cudaMemcpyAsync(nd, c->d_pmats, (size_t)c->pmat_cap * mat, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    dev_free(c, c->d_pmats, (size_t)c->pmat_cap * mat);
+  }
+  c->d_pmats = nd;
+  c->pmat_cap = cap;
+  return 0;
+}
+
+static int check_slots(cb_ctx* c, int count, const int32_t* slots) {
+  REQUIRE(c && slots && count >= 0, "bad argument");
+  for (int i = 0; i < count; ++i)
+    REQUIRE(slots[i] >= 0 && slots[i] < c->pmat_cap, "P slot %d out of range (reserved %d)", slots[i], c->pmat_cap);
+  return 0;
+}
+
+extern "C" int cb_pmat_upload(cb_ctx* c, int count, const int32_t* slots, const double* mats) {
+  if (check_slots(c, count, slots)) return 1;
+  REQUIRE(mats, "null argument");
+  CU(cudaSetDevice(c->device));
+  const size_t mat = (size_t)c->n_states * c->n_states * 8;
+  if (ensure_scratch(c, (size_t)count * mat)) return 1;
+  CU(cudaStreamSynchronize(c->stream));  // scratch reuse
+  memcpy(c->h_scratch, mats, (size_t)count * mat);
+  int i = 0;
+  while (i < count) {  // coalesce runs of consecutive slots into one copy
+    int j = i + 1;
+    while (j < count && slots[j] == slots[j - 1] + 1) ++j;
+    CU(cudaMemcpyAsync(c->d_pmats + (size_t)slots[i] * c->n_states * c->n_states, (char*)c->h_scratch + (size_t)i * mat,
+                       (size_t)(j - i) * mat, cudaMemcpyHostToDevice, c->stream));
+    i = j;
+  }
+  c->h2d += (int64_t)count * mat;
+  return 0;
+}
+
+extern "C" int cb_pmat_download(cb_ctx* c, int count, const int32_t* slots, double* out) {
+  if (check_slots(c, count, slots)) return 1;
+  REQUIRE(out, "null argument");
+  CU(cudaSetDevice(c->device));
+  const size_t mat = (size_t)c->n_states * c->n_states * 8;
+  for (int i = 0; i < count; ++i)
+    CU(cudaMemcpyAsync((char*)out + (size_t)i * mat, c->d_pmats + (size_t)slots[i] * c->n_states * c->n_states, mat,
+                       cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->d2h += (int64_t)count * mat;
+  return 0;
+}
+
+extern "C" int cb_pmat_build(cb_ctx* c, int model, const double* pi, double beta, const double* gtr,
+                             int count, const int32_t* slots, const double* d, const double* x) {
+  if (check_slots(c, count, slots)) return 1;
+  REQUIRE(d, "null argument");
+  REQUIRE(model >= CB_MODEL_JC && model <= CB_MODEL_GTR_EIG, "unknown model %d", model);
+  REQUIRE(model == CB_MODEL_JC || pi, "pi required");
+  REQUIRE(model != CB_MODEL_GTR_EIG || gtr, "GTR eigensystem required");
+  REQUIRE(model != CB_MODEL_F81_BINARY || c->n_states == 2, "binary F81 needs 2 states");
+  if (count == 0) return 0;
+  CU(cudaSetDevice(c->device));
+  const int S = c->n_states;
+  const size_t n_gtr = (model == CB_MODEL_GTR_EIG) ? (size_t)S + 2 * (size_t)S * S : 0;
+  // scratch layout: pi[S] | gtr[n_gtr] | d[count] | x[count] | slots[count] (int32)
+  const size_t doubles = (size_t)S + n_gtr + 2 * (size_t)count;
+  const size_t bytes = doubles * 8 + (size_t)count * 4;
+  if (ensure_scratch(c, bytes)) return 1;
+  CU(cudaStreamSynchronize(c->stream));  // scratch reuse
+  double* h = (double*)c->h_scratch;
+  if (pi) memcpy(h, pi, (size_t)S * 8); else memset(h, 0, (size_t)S * 8);
+  if (n_gtr) memcpy(h + S, gtr, n_gtr * 8);
+  memcpy(h + S + n_gtr, d, (size_t)count * 8);
+  if (x) memcpy(h + S + n_gtr + count, x, (size_t)count * 8);
+  memcpy(h + doubles, slots, (size_t)count * 4);
+  CU(cudaMemcpyAsync(c->d_scratch, c->h_scratch, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->h2d += (int64_t)bytes;
+  const double* dd = (const double*)c->d_scratch;
+  const int threads = (S * S >= 256) ? 256 : ((S * S + 31) / 32 * 32);
+  pmat_build_kernel<<<count, threads, (size_t)S * 8, c->stream>>>(
+      model, S, dd, beta, n_gtr ? dd + S : nullptr, count, (const int32_t*)(dd + doubles), dd + S + n_gtr,
+      x ? dd + S + n_gtr + count : nullptr, c->d_pmats);
+  CU(cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+
+// ------------------------------------------------------------------------ buffers/snapshots
+static int buffer_acquire(cb_ctx* c, int* out) {
+  if (!c->free_buffers.empty()) {
+    *out = c->free_buffers.back();
+    c->free_buffers.pop_back();
+  } else {
+    Buffer b;
+    void* p = nullptr;
+    if (dev_alloc(c, &p, c->buffer_bytes)) return 1;
+    b.data = (double*)p;
+    b.scale = (int32_t*)(b.data + (size_t)c->n_cats * c->n_states * c->P);
+    c->buffers.push_back(b);
+    *out = (int)c->buffers.size() - 1;
+  }
+  c->buffers[*out].refs = 1;
+  return 0;
+}
+static void buffer_release(cb_ctx* c, int b) {
+  if (b < 0) return;
+  if (--c->buffers[b].refs == 0) c->free_buffers.push_back(b);
+}
+static bool snapshot_valid(cb_ctx* c, int s) {
+  return s >= 0 && s < (int)c->snaps.size() && c->snaps[s].refs > 0;
+}
+extern "C" int cb_snapshot_retain(cb_ctx* c, int s) {
+  REQUIRE(c && snapshot_valid(c, s), "invalid snapshot %d", s);
+  c->snaps[s].refs++;
+  return 0;
+}
+extern "C" int cb_snapshot_release(cb_ctx* c, int s) {
+  REQUIRE(c && snapshot_valid(c, s), "invalid snapshot %d", s);
+  if (--c->snaps[s].refs == 0) {
+    for (int32_t b : c->snaps[s].buf_of_node) buffer_release(c, b);
+    c->snaps[s].buf_of_node.clear();
+    c->free_snaps.push_back(s);
+  }
+  return 0;
+}
+
+extern "C" int cb_snapshot_read(cb_ctx* c, int s, int node, double* out, int32_t* scale_out) {
+  REQUIRE(c && out && snapshot_valid(c, s), "invalid snapshot %d", s);
+  const Snapshot& sn = c->snaps[s];
+  REQUIRE(node >= 0 && node < (int)sn.buf_of_node.size() && sn.buf_of_node[node] >= 0,
+          "node %d is not in snapshot %d", node, s);
+  CU(cudaSetDevice(c->device));
+  const Buffer& b = c->buffers[sn.buf_of_node[node]];
+  const int C = c->n_cats, S = c->n_states;
+  const int64_t P = c->P, n = c->n_sites;
+  std::vector<double> tmp((size_t)C * S * P);
+  const size_t n_scale = c->family_s2 ? (size_t)P : (size_t)C * P;
+  std::vector<int32_t> sc(n_scale);
+  CU(cudaMemcpyAsync(tmp.data(), b.data, tmp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(sc.data(), b.scale, n_scale * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->d2h += (int64_t)tmp.size() * 8 + (int64_t)n_scale * 4;
+  for (int k = 0; k < C; ++k)
+    for (int i = 0; i < S; ++i)
+      for (int64_t p = 0; p < n; ++p) {
+        const int e = c->family_s2 ? sc[p] : sc[(size_t)k * P + p];
+        double v = tmp[((size_t)k * S + i) * P + p];
+        if (!scale_out) v = ldexp(v, e);
+        out[((size_t)k * S + i) * n + p] = v;
+      }
+  if (scale_out) {
+    // one exponent per site: categories of the general family are brought to their max
+    for (int64_t p = 0; p < n; ++p) {
+      if (c->family_s2) {
+        scale_out[p] = sc[p];
+      } else {
+        int emax = INT_MIN;
+        for (int k = 0; k < C; ++k) emax = std::max(emax, sc[(size_t)k * P + p]);
+        scale_out[p] = emax;
+        for (int k = 0; k < C; ++k)
+          for (int i = 0; i < S; ++i) {
+            double& v = out[((size_t)k * S + i) * n + p];
+            v = ldexp(v, sc[(size_t)k * P + p] - emax);
+          }
+      }
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- evaluation
+static int ensure_staging(cb_ctx* c, int n_ops, int n_ranges, int n_out) {
+  if (n_ops > c->ops_cap) {
+    int cap = std::max(n_ops, std::max(256, c->ops_cap * 2));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_ops) dev_free(c, c->d_ops, (size_t)c->ops_cap * sizeof(OpDesc));
+    if (c->h_ops) cudaFreeHost(c->h_ops);
+    c->d_ops = nullptr; c->h_ops = nullptr; c->ops_cap = 0;
+    if (dev_alloc(c, (void**)&c->d_ops, (size_t)cap * sizeof(OpDesc))) return 1;
+    CU(cudaMallocHost(&c->h_ops, (size_t)cap * sizeof(OpDesc)));
+    c->ops_cap = cap;
+  }
+  if (n_ranges > c->ranges_cap) {
+    int cap = std::max(n_ranges, std::max(256, c->ranges_cap * 2));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_ranges) dev_free(c, c->d_ranges, (size_t)c->ranges_cap * sizeof(RangeDesc));
+    if (c->h_ranges) cudaFreeHost(c->h_ranges);
+    c->d_ranges = nullptr; c->h_ranges = nullptr; c->ranges_cap = 0;
+    if (dev_alloc(c, (void**)&c->d_ranges, (size_t)cap * sizeof(RangeDesc))) return 1;
+    CU(cudaMallocHost(&c->h_ranges, (size_t)cap * sizeof(RangeDesc)));
+    c->ranges_cap = cap;
+  }
+  if (n_out > c->out_cap) {
+    int cap = std::max(n_out, std::max(1, c->out_cap * 2));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_block_sums) dev_free(c, c->d_block_sums, (size_t)c->out_cap * c->max_blocks * 8);
+    if (c->d_tickets) dev_free(c, c->d_tickets, (size_t)c->out_cap * 4);
+    if (c->d_results) dev_free(c, c->d_results, (size_t)c->out_cap * 8);
+    if (c->d_root_dot) dev_free(c, c->d_root_dot, (size_t)c->out_cap * c->n_cats * c->P * 8);
+    if (c->d_root_exp) dev_free(c, c->d_root_exp, (size_t)c->out_cap * c->n_cats * c->P * 4);
+    if (c->h_results) cudaFreeHost(c->h_results);
+    c->d_block_sums = c->d_results = c->d_root_dot = nullptr;
+    c->d_tickets = nullptr; c->d_root_exp = nullptr; c->h_results = nullptr; c->out_cap = 0;
+    c->max_blocks = (int)(c->P / 32) + 1;
+    if (dev_alloc(c, (void**)&c->d_block_sums, (size_t)cap * c->max_blocks * 8)) return 1;
+    if (dev_alloc(c, (void**)&c->d_tickets, (size_t)cap * 4)) return 1;
+    CU(cudaMemsetAsync(c->d_tickets, 0, (size_t)cap * 4, c->stream));
+    if (dev_alloc(c, (void**)&c->d_results, (size_t)cap * 8)) return 1;
+    if (!c->family_s2) {
+      if (dev_alloc(c, (void**)&c->d_root_dot, (size_t)cap * c->n_cats * c->P * 8)) return 1;
+      if (dev_alloc(c, (void**)&c->d_root_exp, (size_t)cap * c->n_cats * c->P * 4)) return 1;
+    }
+    CU(cudaMallocHost(&c->h_results, (size_t)cap * 8));
+    c->out_cap = cap;
+  }
+  return 0;
+}
+
+static LaunchConst make_const(cb_ctx* c) {
+  LaunchConst k;
+  k.ops = c->d_ops;
+  k.ranges = c->d_ranges;
+  k.pmats = c->d_pmats;
+  k.weights = c->d_weights;
+  k.pi = c->d_pi;
+  k.amb = c->d_amb;
+  k.block_sums = c->d_block_sums;
+  k.tickets = c->d_tickets;
+  k.results = c->d_results;
+  k.root_dot = c->d_root_dot;
+  k.root_exp = c->d_root_exp;
+  k.n_sites = c->P;
+  k.n_states = c->n_states;
+  k.n_cats = c->n_cats;
+  k.code_bytes = c->code_bytes;
+  k.max_blocks = c->max_blocks;
+  k.cats = (double)c->n_cats;
+  return k;
+}
+
+constexpr int MAX_CHAIN_OPS = 160;  // P staging of the 2-state walk: 160 * 256 B = 40 KB
+
+static int general_rows_per_chunk(int S) {
+  // rows of the two P matrices staged per pass (multiple of 4, <= 64).  Prefer a footprint
+  // <= 100 KB (two blocks per SM) as long as that keeps >= 16 rows; else use up to 226 KB.
+  const int rmax = std::min((S + 3) / 4 * 4, 64);
+  for (int R = rmax; R >= std::min(16, rmax); R -= 4)
+    if (gen_smem_bytes(S, R) <= (size_t)100 * 1024) return R;
+  for (int R = rmax; R >= 4; R -= 4)
+    if (gen_smem_bytes(S, R) <= (size_t)226 * 1024) return R;
+  return 0;
+}
+
+// Launch the ranges [r_begin, r_end) (all independent) as one kernel.
+static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end, int max_ops_in_range) {
+  const int n_r = r_end - r_begin;
+  LaunchConst kk = k;
+  kk.ranges = k.ranges + r_begin;
+  if (c->family_s2) {
+    int threads = 256;
+    const int64_t pairs = c->P / 2;
+    while (threads > 64 && pairs * n_r < (int64_t)threads * c->sm_count * 2) threads >>= 1;
+    dim3 grid((unsigned)((pairs + threads - 1) / threads), (unsigned)n_r);
+    const size_t smem = (size_t)max_ops_in_range * 8 * c->n_cats * sizeof(double);
+    if (c->n_cats == 4)
+      prune_s2_kernel<4><<<grid, threads, smem, c->stream>>>(kk);
+    else
+      prune_s2_kernel<1><<<grid, threads, smem, c->stream>>>(kk);
+  } else {
+    const int R = general_rows_per_chunk(c->n_states);
+    REQUIRE(R > 0, "n_states = %d does not fit the shared-memory tiling", c->n_states);
+    dim3 grid((unsigned)(c->P / GEN_T), (unsigned)n_r, (unsigned)c->n_cats);
+    prune_general_kernel<<<grid, GEN_THREADS, gen_smem_bytes(c->n_states, R), c->stream>>>(kk, R);
+  }
+  CU(cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+
+// Shared implementation of cb_eval (n_lists = 1) and cb_eval_batch.
+static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* offsets, const int32_t* nodes,
+                     const int32_t* children, const int32_t* pslots, const double* pi, int flags,
+                     int* snapshot_out, double* lnl_out) {
+  REQUIRE(c && c->n_states > 0, "cb_set_tips must come first");
+  REQUIRE(offsets && nodes && children && pslots && pi, "null argument");
+  REQUIRE(snapshot_in < 0 || snapshot_valid(c, snapshot_in), "invalid snapshot %d", snapshot_in);
+  const int C = c->n_cats, N = c->n_taxa, n_nodes = 2 * N;  // ids 1 .. 2N-1
+  const int total_ops = offsets[n_lists];
+  REQUIRE(total_ops > 0, "empty op list");
+  const bool want_snap = (flags & CB_EVAL_WANT_SNAPSHOT) != 0;
+  const bool store_root = (flags & CB_EVAL_STORE_ROOT) != 0;
+  REQUIRE(!(want_snap && n_lists != 1), "snapshots are only kept for single evaluations");
+  CU(cudaSetDevice(c->device));
+  if (ensure_staging(c, total_ops, total_ops, n_lists)) return 1;
+  CU(cudaEventSynchronize(c->ev_stage));  // previous H2D of the staging area finished
+
+  const Snapshot* sin = snapshot_in >= 0 ? &c->snaps[snapshot_in] : nullptr;
+  c->op_of_node.assign(n_nodes, -1);
+  std::vector<int> new_bufs;   // buffers written by this evaluation (node order = op order)
+  std::vector<int> new_nodes;
+  int n_ranges = 0;
+  std::vector<std::pair<int, int>> launches;  // [range begin, range end) per launch
+  std::vector<int> launch_maxops;
+  bool all_chains = true;
+
+  for (int li = 0; li < n_lists; ++li) {
+    const int b = offsets[li], e = offsets[li + 1];
+    REQUIRE(e > b, "empty op list %d", li);
+    // chain detection: every op after the first consumes the previous op's node through
+    // exactly one child and nothing else produced by this list (a dirty path, ML_gamma.pyx:99-114)
+    for (int i = b; i < e; ++i) {
+      const int node = nodes[i];
+      REQUIRE(node > N && node < n_nodes, "op %d: node %d is not an internal node", i, node);
+      REQUIRE(c->op_of_node[node] < 0, "op %d: node %d is computed twice", i, node);
+      c->op_of_node[node] = i;
+    }
+    bool chain = !(flags & CB_EVAL_FORCE_LEVELS) && (e - b) <= MAX_CHAIN_OPS;
+    for (int i = b; i < e && chain; ++i) {
+      int n_prev = 0;
+      for (int kx = 0; kx < 2; ++kx) {
+        const int ch = children[2 * i + kx];
+        if (ch > N && ch < n_nodes && c->op_of_node[ch] >= b) {
+          if (i > b && c->op_of_node[ch] == i - 1) ++n_prev; else chain = false;
+        }
+      }
+      if (i > b && n_prev != 1) chain = false;
+    }
+    for (int i = b; i < e; ++i) c->op_of_node[nodes[i]] = -1;
+    if (!chain) all_chains = false;
+    REQUIRE(chain || n_lists == 1, "cb_eval_batch: candidate %d is not a chain of at most %d ops", li, MAX_CHAIN_OPS);
+
+    for (int i = b; i < e; ++i) {
+      OpDesc& op = c->h_ops[i];
+      const int node = nodes[i];
+      REQUIRE(node > N && node < n_nodes, "op %d: node %d is not an internal node", i, node);
+      const bool is_root = (i == e - 1);
+      op.is_root = is_root ? 1 : 0;
+      op.pad_ = 0;
+      op.dst = nullptr;
+      op.dst_scale = nullptr;
+      const bool keep = is_root ? (want_snap && store_root) : (want_snap || !chain);
+      if (keep) {
+        int bi;
+        if (buffer_acquire(c, &bi)) return 1;
+        op.dst = c->buffers[bi].data;
+        op.dst_scale = c->buffers[bi].scale;
+        new_bufs.push_back(bi);
+        new_nodes.push_back(node);
+      }
+      for (int kx = 0; kx < 2; ++kx) {
+        const int ch = children[2 * i + kx];
+        op.src[kx] = nullptr;
+        op.src_scale[kx] = nullptr;
+        if (ch >= 1 && ch <= N) {
+          op.kind[kx] = SRC_TIP;
+          op.src[kx] = (const char*)c->d_codes + (size_t)(ch - 1) * c->P * c->code_bytes;
+        } else {
+          REQUIRE(ch > N && ch < n_nodes, "op %d: bad child id %d", i, ch);
+          const int prod = c->op_of_node[ch];
+          if (prod >= b && prod < i) {
+            if (chain && prod == i - 1) {
+              op.kind[kx] = SRC_CARRIED;
+            } else {
+              REQUIRE(c->h_ops[prod].dst, "internal error: producer of node %d has no buffer", ch);
+              op.kind[kx] = SRC_BUFFER;
+              op.src[kx] = c->h_ops[prod].dst;
+              op.src_scale[kx] = c->h_ops[prod].dst_scale;
+            }
+          } else {
+            REQUIRE(sin && ch < (int)sin->buf_of_node.size() && sin->buf_of_node[ch] >= 0,
+                    "op %d: child %d is neither recomputed nor in the input snapshot", i, ch);
+            const Buffer& bf = c->buffers[sin->buf_of_node[ch]];
+            op.kind[kx] = SRC_BUFFER;
+            op.src[kx] = bf.data;
+            op.src_scale[kx] = bf.scale;
+          }
+        }
+        for (int q = 0; q < C; ++q) {
+          const int sl = pslots[(size_t)(2 * i + kx) * C + q];
+          REQUIRE(sl >= 0 && sl < c->pmat_cap, "op %d: P slot %d out of range", i, sl);
+          op.pslot[kx][q] = sl;
+        }
+        for (int q = C; q < CB_MAX_CATS; ++q) op.pslot[kx][q] = 0;
+      }
+      c->op_of_node[node] = i;
+    }
+
+    if (chain) {
+      RangeDesc& r = c->h_ranges[n_ranges++];
+      r.begin = b; r.end = e; r.out_index = li; r.pad_ = 0;
+    } else {
+      // level schedule: level = 1 + max(level of producing ops of the children)
+      c->level_of_op.assign(e - b, 1);
+      int max_level = 1;
+      for (int i = b; i < e; ++i) {
+        int lv = 1;
+        for (int kx = 0; kx < 2; ++kx) {
+          const int ch = children[2 * i + kx];
+          if (ch > N) {
+            const int prod = c->op_of_node[ch];
+            if (prod >= b && prod < i) lv = std::max(lv, c->level_of_op[prod - b] + 1);
+          }
+        }
+        c->level_of_op[i - b] = lv;
+        max_level = std::max(max_level, lv);
+      }
+      c->order.resize(e - b);
+      for (int i = 0; i < e - b; ++i) c->order[i] = i;
+      std::stable_sort(c->order.begin(), c->order.end(),
+                       [&](int a, int bb) { return c->level_of_op[a] < c->level_of_op[bb]; });
+      int pos = 0;
+      for (int lv = 1; lv <= max_level; ++lv) {
+        const int start = n_ranges;
+        while (pos < e - b && c->level_of_op[c->order[pos]] == lv) {
+          const int i = b + c->order[pos++];
+          RangeDesc& r = c->h_ranges[n_ranges++];
+          r.begin = i; r.end = i + 1; r.out_index = (i == e - 1) ? li : -1; r.pad_ = 0;
+        }
+        if (n_ranges > start) {
+          launches.push_back({start, n_ranges});
+          launch_maxops.push_back(1);
+        }
+      }
+    }
+    for (int i = b; i < e; ++i) c->op_of_node[nodes[i]] = -1;
+  }
+  if (all_chains) {
+    int mx = 0;
+    for (int li = 0; li < n_lists; ++li) mx = std::max(mx, offsets[li + 1] - offsets[li]);
+    launches.push_back({0, n_ranges});
+    launch_maxops.push_back(mx);
+  }
+
+  // upload descriptors + pi, launch
+  CU(cudaMemcpyAsync(c->d_ops, c->h_ops, (size_t)total_ops * sizeof(OpDesc), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_ranges, c->h_ranges, (size_t)n_ranges * sizeof(RangeDesc), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_pi, pi, (size_t)c->n_states * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaEventRecord(c->ev_stage, c->stream));
+  c->h2d += (int64_t)total_ops * sizeof(OpDesc) + (int64_t)n_ranges * sizeof(RangeDesc) + c->n_states * 8;
+
+  const LaunchConst k = make_const(c);
+  CU(cudaEventRecord(c->ev0, c->stream));
+  for (size_t li = 0; li < launches.size(); ++li)
+    if (launch_ranges(c, k, launches[li].first, launches[li].second, launch_maxops[li])) return 1;
+  if (!c->family_s2) {
+    dim3 grid((unsigned)((c->P + 255) / 256), (unsigned)n_lists);
+    root_combine_kernel<<<grid, 256, 0, c->stream>>>(k);
+    CU(cudaGetLastError());
+    c->launches += 1;
+  }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  c->timing_valid = true;
+
+  if (c->comm) {
+    int r = g_nccl.AllReduce(c->d_results, c->d_results, (size_t)n_lists, NCCL_DOUBLE, NCCL_SUM, c->comm, c->stream);
+    REQUIRE(r == 0, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  }
+  CU(cudaMemcpyAsync(c->h_results, c->d_results, (size_t)n_lists * 8, cudaMemcpyDeviceToHost, c->stream));
+  c->d2h += (int64_t)n_lists * 8;
+  c->last_n_out = n_lists;
+
+  // bookkeeping (stream-ordered: temporaries may be recycled by later launches on this stream)
+  if (want_snap) {
+    int sid;
+    if (!c->free_snaps.empty()) {
+      sid = c->free_snaps.back();
+      c->free_snaps.pop_back();
+    } else {
+      c->snaps.emplace_back();
+      sid = (int)c->snaps.size() - 1;
+    }
+    Snapshot& sn = c->snaps[sid];
+    sin = snapshot_in >= 0 ? &c->snaps[snapshot_in] : nullptr;  // vector may have moved
+    if (sin) sn.buf_of_node = sin->buf_of_node; else sn.buf_of_node.assign(n_nodes, -1);
+    sn.buf_of_node.resize(n_nodes, -1);
+    sn.refs = 1;
+    for (size_t i = 0; i < new_nodes.size(); ++i) sn.buf_of_node[new_nodes[i]] = -2 - (int)i;  // mark replaced
+    for (int nd = 0; nd < n_nodes; ++nd) {
+      int32_t& bi = sn.buf_of_node[nd];
+      if (bi >= 0) c->buffers[bi].refs++;
+      else if (bi <= -2) bi = new_bufs[-2 - bi];  // ownership moves from this evaluation to the snapshot
+    }
+    if (snapshot_out) *snapshot_out = sid;
+  } else {
+    for (int bi : new_bufs) buffer_release(c, bi);
+    if (snapshot_out) *snapshot_out = -1;
+  }
+
+  if (!(flags & CB_EVAL_NO_SYNC)) {
+    CU(cudaStreamSynchronize(c->stream));
+    if (lnl_out) memcpy(lnl_out, c->h_results, (size_t)n_lists * 8);
+  }
+  return 0;
+}
+
+extern "C" int cb_eval(cb_ctx* c, int snapshot_in, int n_ops, const int32_t* nodes, const int32_t* children,
+                       const int32_t* pslots, const double* pi, int flags, int* snapshot_out, double* lnl_out) {
+  const int32_t offsets[2] = {0, n_ops};
+  return eval_impl(c, snapshot_in, 1, offsets, nodes, children, pslots, pi, flags, snapshot_out, lnl_out);
+}
+
+extern "C" int cb_eval_batch(cb_ctx* c, int snapshot_in, int n_batch, const int32_t* op_offsets, const int32_t* nodes,
+                             const int32_t* children, const int32_t* pslots, const double* pi, double* lnl_out) {
+  REQUIRE(n_batch >= 1, "empty batch");
+  return eval_impl(c, snapshot_in, n_batch, op_offsets, nodes, children, pslots, pi, 0, nullptr, lnl_out);
+}
+
+extern "C" int cb_result_wait(cb_ctx* c, double* lnl_out) {
+  REQUIRE(c, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  if (lnl_out && c->h_results) memcpy(lnl_out, c->h_results, (size_t)c->last_n_out * 8);
+  return 0;
+}
+
+// --------------------------------------------------------------------------- introspection
+extern "C" int cb_stats(cb_ctx* c, int64_t* launches, int64_t* h2d, int64_t* d2h, int64_t* dev_bytes) {
+  REQUIRE(c, "null argument");
+  if (launches) *launches = c->launches;
+  if (h2d) *h2d = c->h2d;
+  if (d2h) *d2h = c->d2h;
+  if (dev_bytes) *dev_bytes = c->dev_bytes;
+  return 0;
+}
+extern "C" int cb_last_eval_ms(cb_ctx* c, float* ms) {
+  REQUIRE(c && ms && c->timing_valid, "no evaluation has been timed");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->ev1));
+  CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return 0;
+}
+extern "C" int cb_sync(cb_ctx* c) {
+  REQUIRE(c, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int cb_flush_l2(cb_ctx* c) {
+  REQUIRE(c, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (!c->d_flush) {
+    c->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+    if (dev_alloc(c, &c->d_flush, c->flush_bytes)) return 1;
+  }
+  CU(cudaMemsetAsync(c->d_flush, 0x5a, c->flush_bytes, c->stream));
+  return 0;
+}

@@ -1,0 +1,284 @@
+"""Tree log-likelihood surfaces: ``matML`` / ``cache_matML`` of ML_gamma.pyx and ML.pyx on the GPU.
+
+The reference walks the edge list in Python and calls NumPy ``dot`` per edge and category
+(ML_gamma.pyx:22-38).  Here the edge list is turned once into a node-operation list
+(children before parents), the P-matrix slots of every (edge, category) are gathered, and one
+``cb_eval`` call runs the whole pass on the device: one launch per tree level for a full
+evaluation, a single launch for a dirty path.  The returned cache is an opaque device
+snapshot (the driver only hands it back, mat_mcmc_gamma.py:52,149,196); indexing it
+(``cache[k][node]``) downloads the reference-shaped (S, n_sites) array.
+"""
+from __future__ import annotations
+
+import os
+from operator import itemgetter
+
+import numpy as np
+
+from . import config, subst
+from .alignment import LeafMatrices, compress_patterns
+from .engine import Engine
+from .subst import PMatTable, table_from_host
+
+# ---------------------------------------------------------------------------- engines
+_engines = {}  # (id(ll_mats), n_cats) -> (ll_mats, Engine, site_to_pattern or None)
+COMPRESS_MAX_SITES = int(os.environ.get("CYBAYES_COMPRESS_MAX_SITES", "250000"))
+_engine_factory = Engine  # tests substitute a fake engine here
+
+
+def _codes_from_dense(ll_mats, n_taxa):
+    """State codes from reference-style 0/1 float matrices (any dict id -> (S, P) array)."""
+    first = np.asarray(ll_mats[1])
+    S, P = first.shape
+    amb_index, amb_rows = {}, [np.ones(S)]
+    codes = np.empty((n_taxa, P), dtype=np.int64)
+    weights_vec = np.arange(S)
+    for t in range(1, n_taxa + 1):
+        m = np.asarray(ll_mats[t])
+        if m.shape != (S, P) or not np.isin(m, (0.0, 1.0)).all():
+            raise ValueError("leaf matrices must be 0/1 arrays of shape (n_states, n_sites)")
+        count = m.sum(axis=0)
+        code = (m * weights_vec[:, None]).sum(axis=0).astype(np.int64)
+        code[count == S] = S
+        for p in np.nonzero((count != 1) & (count != S))[0]:
+            members = tuple(np.nonzero(m[:, p])[0])
+            if not members:
+                raise ValueError("leaf column with no admissible state")
+            if members not in amb_index:
+                amb_index[members] = len(amb_rows)
+                amb_rows.append(m[:, p].astype(np.float64))
+            code[p] = S + amb_index[members]
+        codes[t - 1] = code
+    dtype = np.uint8 if S + len(amb_rows) <= 256 else np.uint16
+    return codes.astype(dtype), S, np.array(amb_rows)
+
+
+def engine_for(ll_mats, n_cats):
+    """The device context holding `ll_mats` (uploaded once, keyed on object identity -- the
+    driver always passes the same config.LEAF_LLMAT, mat_mcmc_gamma.py:55,149)."""
+    key = (id(ll_mats), int(n_cats))
+    hit = _engines.get(key)
+    if hit is not None and hit[0] is ll_mats:
+        return hit[1], hit[2]
+    if isinstance(ll_mats, LeafMatrices):
+        codes, S, amb = ll_mats.codes, ll_mats.n_states, ll_mats.amb_sets
+    else:
+        codes, S, amb = _codes_from_dense(ll_mats, len(ll_mats))
+    site_map, weights = None, None
+    if codes.shape[1] <= COMPRESS_MAX_SITES:
+        pat, w, smap = compress_patterns(codes)
+        if pat.shape[1] < codes.shape[1]:
+            codes, weights, site_map = pat, w, smap
+    eng = _engine_factory(codes, S, n_cats, amb, weights)
+    _engines[key] = (ll_mats, eng, site_map)
+    return eng, site_map
+
+
+def _default_engine(n_cats=None):
+    """Engine of the driver's alignment (config.LEAF_LLMAT) for the substitution builders."""
+    eng, _ = engine_for(config.LEAF_LLMAT, config.N_CATS if n_cats is None else n_cats)
+    return eng
+
+
+subst._engine_hook = _default_engine
+
+
+def reset_engines():
+    """Drop every device context (tests, or a driver that loads another alignment)."""
+    for _, eng, _ in _engines.values():
+        try:
+            eng.close()
+        except Exception:
+            pass
+    _engines.clear()
+
+
+# ------------------------------------------------------------------------------ plans
+class _Plan:
+    """Edge list -> node operations.  `nodes[i]` is completed by the i-th op in the order in
+    which the reference finishes parents while walking `edges` (ML_gamma.pyx:24-36)."""
+    __slots__ = ("edges", "nodes", "children", "edge_keys", "kids", "index")
+
+    def __init__(self, edges):
+        self.edges = list(edges)
+        first = {}
+        nodes, children, kids = [], [], {}
+        for parent, child in self.edges:
+            if parent in first:
+                c0 = first.pop(parent)
+                kids[parent] = (c0, child)
+                nodes.append(parent)
+                children.append(c0)
+                children.append(child)
+            else:
+                first[parent] = child
+        if first:
+            raise ValueError(f"nodes with a single child edge: {sorted(first)}")
+        self.kids = kids
+        self.index = {n: i for i, n in enumerate(nodes)}
+        self.nodes = np.array(nodes, dtype=np.int32)
+        self.children = np.array(children, dtype=np.int32)
+        self.edge_keys = [(n, c) for n in nodes for c in kids[n]]
+
+
+_plan_cache = []  # small MRU list of plans, matched by list equality
+
+
+def _plan_for(edges):
+    for i, p in enumerate(_plan_cache):
+        if p.edges == edges:
+            if i:
+                _plan_cache.insert(0, _plan_cache.pop(i))
+            return p
+    p = _Plan(edges)
+    _plan_cache.insert(0, p)
+    del _plan_cache[4:]
+    return p
+
+
+def _slot_matrix(engine, tmats, edge_keys):
+    """(n_edges, C) int32 P-slot table for the ops' edges."""
+    cols = []
+    getter = itemgetter(*edge_keys) if len(edge_keys) > 1 else None
+    keep = []
+    for t in tmats:
+        if not isinstance(t, PMatTable):
+            t = table_from_host(engine, t)   # reference-style host matrices: upload (host buffers)
+            keep.append(t)
+        elif t.engine is not engine:
+            raise ValueError("transition matrices belong to a different alignment")
+        cols.append(getter(t._slots) if getter else (t._slots[edge_keys[0]],))
+    return np.ascontiguousarray(np.array(cols, dtype=np.int32).T), keep
+
+
+class _CategoryView:
+    def __init__(self, cache, k):
+        self._cache, self._k = cache, k
+
+    def __getitem__(self, node):
+        return self._cache.partial(node)[self._k]
+
+    def keys(self):
+        return self._cache.nodes()
+
+
+class PartialCache:
+    """Opaque snapshot of all internal-node partials on the device (the second return value of
+    matML / cache_matML).  ``cache[k][node]`` gives the reference's (S, n_sites) array."""
+
+    def __init__(self, engine, snap, site_map, node_ids):
+        self.engine, self.snap, self._site_map, self._nodes = engine, snap, site_map, node_ids
+
+    def partial(self, node):
+        a = self.engine.read_partial(self.snap, node)
+        return a if self._site_map is None else a[:, :, self._site_map]
+
+    def partial_scaled(self, node):
+        a, e = self.engine.read_partial(self.snap, node, with_scale=True)
+        if self._site_map is not None:
+            a, e = a[:, :, self._site_map], e[self._site_map]
+        return a, e
+
+    def nodes(self):
+        return list(self._nodes)
+
+    def __getitem__(self, k):
+        if not 0 <= k < self.engine.n_cats:
+            raise IndexError(k)
+        return _CategoryView(self, k)
+
+    def __len__(self):
+        return self.engine.n_cats
+
+    def __del__(self):
+        try:
+            self.engine.release_snapshot(self.snap)
+        except Exception:
+            pass
+
+
+STORE_ROOT = os.environ.get("CYBAYES_STORE_ROOT", "0") == "1"
+
+
+def _full(pi, root, ll_mats, edges, tmats, n_cats_tables):
+    engine, site_map = engine_for(ll_mats, n_cats_tables)
+    plan = _plan_for(edges)
+    if plan.nodes[-1] != root:
+        raise KeyError(root)
+    pslots, keep = _slot_matrix(engine, tmats, plan.edge_keys)
+    lnl, snap = engine.eval(None, plan.nodes, plan.children, pslots, np.asarray(pi, dtype=np.float64),
+                            want_snapshot=True, store_root=STORE_ROOT)
+    nodes = plan.nodes if STORE_ROOT else plan.nodes[:-1]
+    return np.float64(lnl), PartialCache(engine, snap, site_map, nodes.tolist())
+
+
+def _dirty(pi, root, ll_mats, cache, nodes_recompute, edges, tmats, n_cats_tables):
+    engine, site_map = engine_for(ll_mats, n_cats_tables)
+    if not isinstance(cache, PartialCache) or cache.engine is not engine:
+        raise TypeError("cache_LL_Mats must be the cache returned by matML/cache_matML for this alignment")
+    plan = _plan_for(edges)
+    index, kids = plan.index, plan.kids
+    todo = sorted(set(nodes_recompute), key=index.__getitem__)
+    if not todo or todo[-1] != root:
+        todo = sorted(set(todo) | {root}, key=index.__getitem__)  # the root partial is never cached
+    nodes = np.array(todo, dtype=np.int32)
+    children = np.array([c for n in todo for c in kids[n]], dtype=np.int32)
+    edge_keys = [(n, c) for n in todo for c in kids[n]]
+    pslots, keep = _slot_matrix(engine, tmats, edge_keys)
+    lnl, snap = engine.eval(cache.snap, nodes, children, pslots, np.asarray(pi, dtype=np.float64),
+                            want_snapshot=True, store_root=STORE_ROOT)
+    return np.float64(lnl), PartialCache(engine, snap, site_map, cache.nodes())
+
+
+# --------------------------------------------------------- ML_gamma.pyx surface (Gamma rates)
+def matML(pi, root, ll_mats, edges, tmats, n_sites, n_taxa, n_cats):
+    """Full pruning pass over all rate categories (ML_gamma.pyx:7-42).  Returns (lnL, cache)."""
+    return _full(pi, root, ll_mats, edges, tmats, len(tmats))
+
+
+matML_cython = matML  # ML_gamma.pyx:44-79 is the same computation
+
+
+def cache_matML(pi, root, ll_mats, cache_LL_Mats, nodes_recompute, edges, tmats, n_sites, n_taxa, n_cats):
+    """Dirty-path pass: only `nodes_recompute` are recomputed, the rest comes from the cache
+    (ML_gamma.pyx:83-118).  Returns (lnL, new cache); the input cache stays valid."""
+    return _dirty(pi, root, ll_mats, cache_LL_Mats, nodes_recompute, edges, tmats, len(tmats))
+
+
+def score_proposals(pi, root, ll_mats, cache_LL_Mats, proposals):
+    """Extension (no reference entry point): lnL of many candidate proposals against one cache in
+    a single launch.  `proposals` = iterable of (nodes_recompute, edges, tmats) as they would be
+    passed to cache_matML.  Returns an array of lnL, one per candidate."""
+    proposals = list(proposals)
+    n_tables = len(proposals[0][2])
+    engine, _ = engine_for(ll_mats, n_tables)
+    if not isinstance(cache_LL_Mats, PartialCache) or cache_LL_Mats.engine is not engine:
+        raise TypeError("cache must come from matML/cache_matML for this alignment")
+    offsets, all_nodes, all_children, all_slots, keep_all = [0], [], [], [], []
+    for nodes_recompute, edges, tmats in proposals:
+        plan = _plan_for(edges)
+        todo = sorted(set(nodes_recompute) | {root}, key=plan.index.__getitem__)
+        edge_keys = [(n, c) for n in todo for c in plan.kids[n]]
+        pslots, keep = _slot_matrix(engine, tmats, edge_keys)
+        keep_all.append(keep)
+        all_nodes.extend(todo)
+        all_children.extend(c for n in todo for c in plan.kids[n])
+        all_slots.append(pslots)
+        offsets.append(len(all_nodes))
+    return engine.eval_batch(cache_LL_Mats.snap, np.array(offsets, dtype=np.int32),
+                             np.array(all_nodes, dtype=np.int32), np.array(all_children, dtype=np.int32),
+                             np.ascontiguousarray(np.concatenate(all_slots, axis=0)),
+                             np.asarray(pi, dtype=np.float64))
+
+
+# ------------------------------------------------------------------ ML.pyx surface (one rate)
+def matML_single(state, taxa, ll_mats):
+    """ML.matML (ML.pyx:5-49): single rate category, arguments read from the state dict."""
+    lnl, cache = _full(state["pi"], state["root"], ll_mats, state["postorder"], [state["transitionMat"]], 1)
+    return lnl, cache
+
+
+def cache_matML_single(state, taxa, ll_mats, cache_LL_Mat, nodes_recompute):
+    """ML.cache_matML (ML.pyx:51-83)."""
+    return _dirty(state["pi"], state["root"], ll_mats, cache_LL_Mat, nodes_recompute, state["postorder"],
+                  [state["transitionMat"]], 1)

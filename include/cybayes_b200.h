@@ -1,0 +1,133 @@
+/*
+ * cybayes_b200 -- C ABI of the B200-native Felsenstein-pruning likelihood engine.
+ *
+ * This is the drop-in boundary for the one hot path of PhyloStar/CyBayes.  The reference
+ * has no FFI of its own (it is Cython + NumPy, one process, no device); the functions
+ * below are what a reference-side binding for this path binds instead of the bodies of
+ *
+ *   ML_gamma.matML          (ML_gamma.pyx:7-42)     -> cb_eval (full op list, no input snapshot)
+ *   ML_gamma.cache_matML    (ML_gamma.pyx:83-118)   -> cb_eval (dirty-path op list + input snapshot)
+ *   ML.matML / cache_matML  (ML.pyx:5-49, 51-83)    -> the same two, context created with n_cats = 1
+ *   get_prob_t and friends  (mcmc_gamma.pyx:439-547) -> cb_pmat_build (all edges x categories, one launch)
+ *   get_edge_transition_mat (mcmc_gamma.pyx:372-401) -> cb_pmat_build (count = 1..8) or cb_pmat_upload
+ *   utils.sites2Mat output  (utils.pyx:94-120)       -> cb_set_tips (state codes instead of 0/1 fp64 matrices)
+ *   the final np.sum(np.log(ll)) (ML_gamma.pyx:38,40) -> fused into the root node's kernel
+ *   (no reference entry point)                       -> cb_eval_batch: many candidate dirty paths, one launch
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; cb_last_error() gives the
+ *     message of the last failure on the calling thread.  There is no CPU fallback: without
+ *     a CUDA device cb_create fails.
+ *   - all pointers are HOST pointers to caller-owned, C-contiguous buffers that only need to
+ *     stay valid for the duration of the call.  Integers are int32_t unless stated, reals are
+ *     double.  No torch / numpy types cross this boundary.
+ *   - node ids follow the reference: tips 1..n_taxa (file order), internal nodes
+ *     n_taxa+1 .. 2*n_taxa-1 (mcmc_gamma.pyx:265-303), the root is whatever the caller names.
+ *   - a context is single-threaded (the reference is, utils.pyx:3-7); one context drives one GPU.
+ *     Site patterns shard across GPUs as one context (= one process) per GPU with a scalar NCCL
+ *     all-reduce per evaluation (cb_comm_init).
+ */
+#ifndef CYBAYES_B200_H
+#define CYBAYES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_MAX_CATS 8
+
+typedef struct cb_ctx cb_ctx;
+
+/* substitution-model kinds for cb_pmat_build */
+enum {
+  CB_MODEL_JC = 0,         /* ptJC        mcmc_gamma.pyx:507-514 */
+  CB_MODEL_F81 = 1,        /* ptF81       mcmc_gamma.pyx:527-547 */
+  CB_MODEL_F81_BINARY = 2, /* binaryptF81 mcmc_gamma.pyx:516-525 */
+  CB_MODEL_GTR_EIG = 3     /* U exp(lambda d) U^-1; replaces scipy expm at mcmc_gamma.pyx:481 */
+};
+
+/* flags for cb_eval */
+enum {
+  CB_EVAL_WANT_SNAPSHOT = 1, /* keep the recomputed partials and return a new snapshot id      */
+  CB_EVAL_STORE_ROOT = 2,    /* also store the root partial (the reference caches it; the fused */
+                             /* root kernel does not need it)                                   */
+  CB_EVAL_NO_SYNC = 4,       /* enqueue only; the result is read later with cb_result_wait      */
+  CB_EVAL_FORCE_LEVELS = 8   /* never use the single-launch path walk, even for a chain         */
+};
+
+const char* cb_last_error(void);
+int cb_version(void);
+int cb_device_count(int* count_out);
+
+/* ---- context ------------------------------------------------------------------------ */
+int cb_create(int device, cb_ctx** ctx_out);
+int cb_destroy(cb_ctx* ctx);
+
+/* Site-sharded multi-GPU: rank 0 makes a 128-byte NCCL unique id, every rank passes it in.
+ * After this, every cb_eval / cb_eval_batch result is the NCCL all-reduced sum over ranks. */
+int cb_nccl_unique_id(void* id128_out);
+int cb_comm_init(cb_ctx* ctx, const void* id128, int rank, int n_ranks);
+
+/* ---- alignment (leaf data) ------------------------------------------------------------
+ * codes[n_taxa][n_sites], uint8 when code_bytes == 1, uint16 when 2: code < n_states is
+ * that state (one-hot column of utils.pyx:108-111); code = n_states + k selects row k of
+ * amb_sets[n_amb][n_states] (0/1 doubles): k = 0 must be the all-ones set of '?' / '-'
+ * (utils.pyx:99-100), further rows are the 'a/b' multi-hot sets (utils.pyx:102-106).
+ * weights[n_sites] (NULL = all 1.0) are the site-pattern multiplicities.                */
+int cb_set_tips(cb_ctx* ctx, int n_taxa, int64_t n_sites, int n_states, int n_cats,
+                const void* codes, int code_bytes, const double* amb_sets, int n_amb,
+                const double* weights);
+
+/* ---- transition matrices ---------------------------------------------------------------
+ * Device pool of S x S row-major matrices, P[i][j] = Pr(parent i -> child j)
+ * (used as P.dot(child) in ML_gamma.pyx:27).  Slot ids are chosen by the caller. */
+int cb_pmat_reserve(cb_ctx* ctx, int n_slots);
+int cb_pmat_upload(cb_ctx* ctx, int count, const int32_t* slots, const double* mats);
+int cb_pmat_download(cb_ctx* ctx, int count, const int32_t* slots, double* mats_out);
+/* d[count] = branch length * category rate.  x[count] (may be NULL) = exp(-beta*d) computed by
+ * the host libm so JC/F81 matrices equal the reference's bit for bit; NULL = exp on device.
+ * gtr = { lambda[S], U[S][S], Uinv[S][S] } for CB_MODEL_GTR_EIG, else NULL.              */
+int cb_pmat_build(cb_ctx* ctx, int model, const double* pi, double beta, const double* gtr,
+                  int count, const int32_t* slots, const double* d, const double* x);
+
+/* ---- evaluation --------------------------------------------------------------------------
+ * An evaluation is a list of node operations in children-before-parents order:
+ *   nodes[i]            the internal node recomputed by op i
+ *   children[2i..2i+1]  its two children (tip id <= n_taxa, or internal node id)
+ *   pslots[(2i+k)*n_cats + c]  P slot of edge (nodes[i], children[2i+k]) for category c
+ * An internal child that is not produced by an earlier op of the list is read from
+ * snapshot_in (cache_matML's aliasing, ML_gamma.pyx:114).  The last op must be the root.
+ * lnL = sum_p w_p * log( sum_c pi . L_root,c[:,p] / n_cats )          (ML_gamma.pyx:38,40)
+ * computed with exact power-of-two per-site rescaling (the reference has none).         */
+int cb_eval(cb_ctx* ctx, int snapshot_in, int n_ops, const int32_t* nodes,
+            const int32_t* children, const int32_t* pslots, const double* pi, int flags,
+            int* snapshot_out, double* lnl_out);
+/* n_batch independent candidate op lists against the same snapshot; each list must be a
+ * chain (every op after the first consumes the previous op's node).  No snapshot is kept. */
+int cb_eval_batch(cb_ctx* ctx, int snapshot_in, int n_batch, const int32_t* op_offsets,
+                  const int32_t* nodes, const int32_t* children, const int32_t* pslots,
+                  const double* pi, double* lnl_out);
+int cb_result_wait(cb_ctx* ctx, double* lnl_out);
+
+int cb_snapshot_retain(cb_ctx* ctx, int snapshot);
+int cb_snapshot_release(cb_ctx* ctx, int snapshot);
+/* out[n_cats][n_states][n_sites] unscaled = stored * 2^scale; scale_out[n_sites] may be NULL,
+ * in which case the scaling is folded back into out (may underflow, like the reference). */
+int cb_snapshot_read(cb_ctx* ctx, int snapshot, int node, double* out, int32_t* scale_out);
+
+/* ---- introspection / measurement ---------------------------------------------------------- */
+int cb_stats(cb_ctx* ctx, int64_t* kernel_launches, int64_t* bytes_h2d, int64_t* bytes_d2h,
+             int64_t* device_bytes_in_use);
+/* device time in ms of the kernels of the last synchronous cb_eval / cb_eval_batch
+ * (CUDA events on the launching stream) */
+int cb_last_eval_ms(cb_ctx* ctx, float* ms_out);
+int cb_sync(cb_ctx* ctx);
+/* bench helpers: write > L2 bytes to flush it; fill tips on device with a tree simulation */
+int cb_flush_l2(cb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CYBAYES_B200_H */
