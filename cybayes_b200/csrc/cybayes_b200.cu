@@ -90,7 +90,7 @@ struct Snapshot {
 struct cb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr, ev_mark[2] = {nullptr, nullptr};
   int sm_count = 148;
   // alignment
   int n_taxa = 0, n_states = 0, n_cats = 0, code_bytes = 1, n_amb = 0;
@@ -175,6 +175,8 @@ extern "C" int cb_create(int device, cb_ctx** out) {
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
   CU(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
+  CU(cudaEventCreate(&c->ev_mark[0]));
+  CU(cudaEventCreate(&c->ev_mark[1]));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -226,6 +228,8 @@ extern "C" int cb_destroy(cb_ctx* c) {
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaEventDestroy(c->ev_stage);
+  cudaEventDestroy(c->ev_mark[0]);
+  cudaEventDestroy(c->ev_mark[1]);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -591,7 +595,7 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
   if (c->family_s2) {
     int threads = 256;
     const int64_t pairs = c->P / 2;
-    while (threads > 64 && pairs * n_r < (int64_t)threads * c->sm_count * 2) threads >>= 1;
+    while (threads > 64 && pairs < (int64_t)threads * c->sm_count * 2) threads >>= 1;  // independent of n_r: fixed reduction order
     dim3 grid((unsigned)((pairs + threads - 1) / threads), (unsigned)n_r);
     const size_t smem = (size_t)max_ops_in_range * 8 * c->n_cats * sizeof(double);
     if (c->n_cats == 4)
@@ -859,6 +863,19 @@ extern "C" int cb_last_eval_ms(cb_ctx* c, float* ms) {
   CU(cudaSetDevice(c->device));
   CU(cudaEventSynchronize(c->ev1));
   CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return 0;
+}
+extern "C" int cb_mark(cb_ctx* c, int which) {
+  REQUIRE(c && (which == 0 || which == 1), "bad argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->ev_mark[which], c->stream));
+  return 0;
+}
+extern "C" int cb_mark_elapsed_ms(cb_ctx* c, float* ms) {
+  REQUIRE(c && ms, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->ev_mark[1]));
+  CU(cudaEventElapsedTime(ms, c->ev_mark[0], c->ev_mark[1]));
   return 0;
 }
 extern "C" int cb_sync(cb_ctx* c) {

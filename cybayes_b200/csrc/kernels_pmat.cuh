@@ -6,7 +6,7 @@
 // closed forms use explicit __dmul_rn/__dadd_rn: given the same x = exp(-beta d) the
 // matrices are bit-identical to the reference's.  x may come from the host libm
 // (bit-exact mode) or be computed here.  GTR replaces scipy.linalg.expm(Q d)
-// (mcmc_gamma.pyx:481) by U diag(exp(lambda d)) U^-1 from one symmetric
+// (mcmc_gamma.pyx:481) by I + U diag(expm1(lambda d)) U^-1 from one symmetric
 // eigendecomposition per (pi, rates) done on the host.
 #pragma once
 #include "cb_types.cuh"
@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) pmat_build_kernel(int model, int S, const
                                                          int count, const int32_t* __restrict__ slots,
                                                          const double* __restrict__ d, const double* __restrict__ x_in,
                                                          double* __restrict__ pmats) {
-  extern __shared__ double ek[];  // GTR: exp(lambda_k d)
+  extern __shared__ double ek[];  // GTR: expm1(lambda_k d)
   const int m = blockIdx.x;
   if (m >= count) return;
   double* out = pmats + (int64_t)slots[m] * S * S;
@@ -27,13 +27,15 @@ __global__ void __launch_bounds__(256) pmat_build_kernel(int model, int S, const
     const double* lam = gtr;
     const double* U = gtr + S;
     const double* Ui = gtr + S + (int64_t)S * S;
-    for (int q = threadIdx.x; q < S; q += blockDim.x) ek[q] = exp(lam[q] * dd);
+    // P = I + U diag(expm1(lambda d)) U^-1: on short branches the small off-diagonal entries are
+    // sums of O(d) terms instead of differences of O(1) terms (no cancellation against I).
+    for (int q = threadIdx.x; q < S; q += blockDim.x) ek[q] = expm1(lam[q] * dd);
     __syncthreads();
     for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
       const int i = idx / S, j = idx - i * S;
       double acc = 0.0;
       for (int q = 0; q < S; ++q) acc = fma(U[i * S + q] * ek[q], Ui[q * S + j], acc);
-      out[idx] = acc;
+      out[idx] = (i == j) ? 1.0 + acc : acc;
     }
     return;
   }

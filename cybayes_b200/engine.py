@@ -219,6 +219,14 @@ class Engine(SlotPool):
         check(self._lib.cb_last_eval_ms(self._ctx, C.byref(ms)))
         return float(ms.value)
 
+    def mark(self, which):
+        check(self._lib.cb_mark(self._ctx, int(which)))
+
+    def mark_elapsed_ms(self):
+        ms = C.c_float()
+        check(self._lib.cb_mark_elapsed_ms(self._ctx, C.byref(ms)))
+        return float(ms.value)
+
     def sync(self):
         check(self._lib.cb_sync(self._ctx))
 

@@ -123,8 +123,11 @@ int cb_stats(cb_ctx* ctx, int64_t* kernel_launches, int64_t* bytes_h2d, int64_t*
 /* device time in ms of the kernels of the last synchronous cb_eval / cb_eval_batch
  * (CUDA events on the launching stream) */
 int cb_last_eval_ms(cb_ctx* ctx, float* ms_out);
+/* CUDA events on the engine's stream: cb_mark(ctx, 0) ... work ... cb_mark(ctx, 1); elapsed = device ms */
+int cb_mark(cb_ctx* ctx, int which);
+int cb_mark_elapsed_ms(cb_ctx* ctx, float* ms_out);
 int cb_sync(cb_ctx* ctx);
-/* bench helpers: write > L2 bytes to flush it; fill tips on device with a tree simulation */
+/* bench helper: write 256 MB (> the 126 MB L2) to flush it */
 int cb_flush_l2(cb_ctx* ctx);
 
 #ifdef __cplusplus

@@ -6,7 +6,7 @@
 #
 # The reference builds in place (setup.py build_ext --inplace, setup.py:7-8), and
 # /root/reference is read-only, so the build happens in a throw-away temp dir and
-# only the compiled artefacts (.so, .pyc) are kept.  No reference source file is
+# only the compiled artefacts (.so, byte-compiled .code) are kept.  No reference source file is
 # copied into the repository.
 set -euo pipefail
 REF=${1:-/root/reference}
@@ -22,7 +22,7 @@ cp -r "$REF"/. "$TMP"/
 chmod -R u+w "$TMP"
 ( cd "$TMP" && python3 setup.py build_ext --inplace > "$TMP/build.log" 2>&1 ) || { tail -30 "$TMP/build.log"; exit 1; }
 mkdir -p "$OUT"
-rm -f "$OUT"/*.so "$OUT"/*.pyc
+rm -f "$OUT"/*.so "$OUT"/*.pyc "$OUT"/*.code
 for m in ML ML_gamma mcmc mcmc_gamma utils config; do
   cp "$TMP"/$m.*.so "$OUT"/
 done
@@ -31,6 +31,6 @@ python3 - "$TMP" "$OUT" <<'PY'
 import py_compile, sys
 tmp, out = sys.argv[1:3]
 for drv in ("mat_mcmc_gamma", "mat_mcmc"):
-    py_compile.compile(f"{tmp}/{drv}.py", cfile=f"{out}/{drv}.pyc", doraise=True)
+    py_compile.compile(f"{tmp}/{drv}.py", cfile=f"{out}/{drv}.code", doraise=True)
 PY
 echo "build_ref: wrote $(ls "$OUT" | tr '\n' ' ')"

@@ -179,7 +179,7 @@ def p_matrix(model, binary, pi, er, beta, d, gtr_via="expm", Q=None):
         if gtr_via == "expm":
             return _linalg.expm(Q * d)
         lam, U, Uinv = gtr_eigensystem(Q, pi)
-        return (U * np.exp(lam * d)) @ Uinv
+        return np.eye(S) + (U * np.expm1(lam * d)) @ Uinv
     raise ValueError(model)
 
 
@@ -200,6 +200,9 @@ def prob_t(model, binary, pi, tree, er, mean_rate, beta=None, gtr_via="expm"):
     JC uses the caller's beta (config.NORM_BETA, set at :580); F81 recomputes it (:467)."""
     if model == "F81":
         beta = f81_beta(pi)
+    if model == "GTR" and gtr_via == "expm":
+        Q = gtr_q(er, pi)
+        return {e: _linalg.expm(Q * t * mean_rate) for e, t in tree.items()}  # (Q*t)*r as at :481
     Q = gtr_q(er, pi) if model == "GTR" else None
     return {e: p_matrix(model, binary, pi, er, beta, t * mean_rate, gtr_via, Q) for e, t in tree.items()}
 

@@ -143,7 +143,7 @@ def case_vectors(name, fname, reader, model, dtype):
 def run_trace(name, fname, model, dtype, n_gen):
     """Run the byte-compiled, unmodified driver with -t 1 and keep its per-generation output."""
     out_prefix = f"/tmp/golden_{name}"
-    cmd = [sys.executable, "mat_mcmc_gamma.pyc", "-i", os.path.join(REF_DATA, fname), "-m", model,
+    cmd = [sys.executable, "mat_mcmc_gamma.code", "-i", os.path.join(REF_DATA, fname), "-m", model,
            "-n", str(n_gen), "-t", "1", "-d", dtype, "-o", out_prefix]
     res = subprocess.run(cmd, cwd=REF_BUILD, capture_output=True, text=True, check=True)
     gens, counters, init_lnl = [], [], None

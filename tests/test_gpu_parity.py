@@ -1,0 +1,373 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the reference-facing Python surface
+and the C ABI, against (a) golden vectors recorded from the unmodified reference, (b) the NumPy
+oracle on seeded random inputs, (c) size-independent properties (dirty path == full pass bit for
+bit, level schedule == single-launch walk, batch == one by one, scaled == unscaled).
+
+Tolerances: integer artefacts exact; lnL <= 1e-11 relative for JC / F81 (closed forms, same x),
+<= 1e-9 relative for GTR (eigendecomposition vs the reference's Pade expm), as BASELINE.json states
+(1e-9 relative in fp64)."""
+import io
+import os
+import random
+import runpy
+import sys
+
+import numpy as np
+import pytest
+
+import golden_io
+import pruning_oracle as oracle
+from conftest import REPO, load_trace
+
+pytestmark = pytest.mark.gpu
+
+REL_CLOSED, REL_GTR = 1e-11, 1e-9
+
+
+def _setup_case(case):
+    from cybayes_b200 import config
+    from cybayes_b200.driver import load_alignment
+    load_alignment(golden_io.data_path(case), case["dtype"], case["reader"])
+    config.MODEL, config.NORM_BETA = case["model"], case["norm_beta"]
+    return config
+
+
+ALL_CASES = ["binary_F81", "twoStates_F81", "twoStates_JC", "narrow_F81", "narrow_JC", "narrow_GTR", "broad_F81",
+             "phon_ringe_JC", "phon_ringe_F81", "phon_ringe_GTR", "ie42_JC", "ie42_GTR", "ielex2016_JC",
+             "ielex_multistate_F81", "german_multistate_JC"]
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_golden_full_and_dirty(name, golden_cases, gpu_backend):
+    from cybayes_b200.mcmc_gamma import (adjlist2reverse_nodes_dict, get_edge_transition_mat, get_path2root,
+                                         get_prob_t)
+    from cybayes_b200.ML_gamma import cache_matML, matML
+    case = golden_cases[name]
+    config = _setup_case(case)
+    rel = REL_GTR if case["model"] == "GTR" else REL_CLOSED
+    assert config.ALPHABET == case["alphabet"] and config.TAXA == case["taxa"]
+    tree, pi, rates, edges, site_rates = golden_io.case_state(case)
+    if rates is None:  # too many exchangeabilities to store: JC does not use them
+        rates = np.ones(1)
+    tmats = [get_prob_t(pi, tree, rates, r) for r in site_rates]
+    args = (config.N_SITES, config.N_TAXA, config.N_CATS)
+    lnl, cache = matML(pi, case["root"], config.LEAF_LLMAT, edges, tmats, *args)
+    assert abs(lnl - case["lnL"]) <= rel * abs(case["lnL"]), (lnl, case["lnL"])
+    # P(t) sample
+    for key, mats in case["pmat_sample"].items():
+        e = tuple(int(x) for x in key.split(","))
+        for k, ref in enumerate(mats):
+            got = np.asarray(tmats[k][e])
+            if isinstance(ref, dict):
+                np.testing.assert_allclose(got[0], ref["row0"], rtol=1e-9 if case["model"] == "GTR" else 0, atol=1e-15 if case["model"] == "GTR" else 0)
+                np.testing.assert_allclose(np.diag(got), ref["diag"], rtol=1e-9 if case["model"] == "GTR" else 0, atol=0)
+            elif case["model"] == "GTR":
+                np.testing.assert_allclose(got, np.array(ref), rtol=1e-9, atol=1e-15)
+            else:
+                assert np.array_equal(got, np.array(ref)), (key, k)  # bit-identical closed forms
+    # cached partials: per node, per category sums over states and sites
+    some = sorted(case["partial_sums"], key=int)
+    for node in some[:: max(1, len(some) // 6)]:
+        if int(node) == case["root"]:
+            continue
+        part = cache.partial(int(node))
+        got = part.sum(axis=(1, 2))
+        np.testing.assert_allclose(got, case["partial_sums"][node], rtol=1e-9 if case["model"] == "GTR" else 1e-12)
+    if "partials" in case:
+        for node, ref in case["partials"].items():
+            if int(node) != case["root"]:
+                np.testing.assert_allclose(cache.partial(int(node)), np.array(ref), rtol=1e-13, atol=0)
+    # dirty-path evaluations recorded from the reference
+    parents = adjlist2reverse_nodes_dict(tree)
+    for d in case["dirty"]:
+        e = tuple(d["edge"])
+        saved = [tmats[k][e] for k in range(len(tmats))]
+        for k, r in enumerate(site_rates):
+            tmats[k][e] = get_edge_transition_mat(pi, rates, d["new_t"] * r)
+        path = get_path2root(parents, e[1], case["root"])
+        assert path == d["path"]
+        l2, c2 = cache_matML(pi, case["root"], config.LEAF_LLMAT, cache, path, edges, tmats, *args)
+        assert abs(l2 - d["lnL"]) <= rel * abs(d["lnL"]), (e, l2, d["lnL"])
+        for k in range(len(tmats)):
+            tmats[k][e] = saved[k]
+    # after restoring, the dirty path over the same nodes reproduces the full pass bit for bit
+    l3, _ = cache_matML(pi, case["root"], config.LEAF_LLMAT, cache, path, edges, tmats, *args)
+    assert l3 == lnl
+
+
+def _random_problem(seed, n_taxa, n_sites, S, n_cats=4, missing=0.1, poly=0.02, bl_mean=0.1):
+    rng = np.random.default_rng(seed)
+    pyr = random.Random(seed)
+    # random topology: join two random subtrees until one is left; ids like the reference
+    nodes = list(range(1, n_taxa + 1))
+    nxt = n_taxa + 1
+    tree = {}
+    while len(nodes) > 1:
+        a = nodes.pop(pyr.randrange(len(nodes)))
+        b = nodes.pop(pyr.randrange(len(nodes)))
+        tree[nxt, a] = float(rng.exponential(bl_mean))
+        tree[nxt, b] = float(rng.exponential(bl_mean))
+        nodes.append(nxt)
+        nxt += 1
+    root = nxt - 1
+    edges = oracle.edge_order(tree, root, n_taxa)
+    amb = [np.ones(S)]
+    if S > 2 and poly > 0:
+        for _ in range(3):
+            v = np.zeros(S)
+            v[rng.choice(S, size=2, replace=False)] = 1.0
+            amb.append(v)
+    amb = np.array(amb)
+    codes = rng.integers(0, S, size=(n_taxa, n_sites))
+    codes[rng.random((n_taxa, n_sites)) < missing] = S
+    if len(amb) > 1:
+        m = rng.random((n_taxa, n_sites)) < poly
+        codes[m] = S + rng.integers(1, len(amb), size=int(m.sum()))
+    codes = codes.astype(np.uint8 if S + len(amb) <= 256 else np.uint16)
+    pi = rng.dirichlet(np.full(S, 5.0))
+    er = rng.dirichlet(np.ones(S * (S - 1) // 2))
+    rates = oracle.site_rates(0.7, n_cats) if n_cats == 4 else [1.0] * n_cats
+    return tree, root, edges, codes, amb, pi, er, rates
+
+
+def _oracle_leaves(codes, S, amb):
+    table = np.vstack([np.eye(S), amb])
+    return {t + 1: np.ascontiguousarray(table[codes[t].astype(np.int64)].T) for t in range(codes.shape[0])}
+
+
+@pytest.mark.parametrize("S,n_taxa,n_sites,model", [(2, 12, 333, "F81"), (2, 40, 1000, "GTR"), (4, 9, 65, "GTR"),
+                                                    (6, 17, 200, "F81"), (23, 14, 129, "JC"), (47, 10, 64, "GTR"),
+                                                    (64, 8, 100, "GTR"), (130, 6, 40, "F81")])
+def test_random_inputs_vs_oracle(S, n_taxa, n_sites, model, gpu_backend):
+    """Engine called directly with host P matrices (cb_pmat_upload) and with device-built ones
+    (cb_pmat_build): lnL, every cached partial and the batched P builder against the oracle."""
+    from cybayes_b200 import _lib
+    from cybayes_b200.engine import Engine
+    from cybayes_b200.likelihood import _Plan
+    from cybayes_b200.subst import gtr_eigensystem
+    tree, root, edges, codes, amb, pi, er, rates = _random_problem(1000 + S, n_taxa, n_sites, S)
+    C = len(rates)
+    leaves = _oracle_leaves(codes, S, amb)
+    beta = oracle.f81_beta(pi)
+    if model == "JC":
+        pi = np.full(S, 1.0 / S)
+        beta = oracle.f81_beta(pi)
+    tm = [oracle.prob_t(model, False, pi, tree, er, r, beta=beta) for r in rates]
+    want, want_cache = oracle.mat_ml(pi, root, leaves, edges, tm, n_sites, n_taxa)
+    want_scaled = oracle.mat_ml_scaled(pi, root, leaves, edges, tm, n_sites, n_taxa)
+    assert abs(want - want_scaled) <= 1e-13 * abs(want)
+
+    eng = Engine(codes, S, C, amb)
+    plan = _Plan(edges)
+    ekeys = list(tree.keys())
+    n_e = len(ekeys)
+    # (a) host matrices uploaded
+    block = eng.alloc_slots(n_e * C)
+    slot_of = {(k, e): block.base + k * n_e + i for k in range(C) for i, e in enumerate(ekeys)}
+    eng.upload_pmats(np.arange(block.base, block.base + n_e * C, dtype=np.int32),
+                     np.stack([tm[k][e] for k in range(C) for e in ekeys]))
+    pslots = np.array([[slot_of[k, e] for k in range(C)] for e in plan.edge_keys], dtype=np.int32)
+    lnl, snap = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=True, store_root=True)
+    assert abs(lnl - want) <= 1e-12 * abs(want), (lnl, want)
+    for node in plan.nodes.tolist():
+        got = eng.read_partial(snap, node)
+        ref = np.stack([want_cache[k][node] for k in range(C)])
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0)
+    # (b) device-built matrices
+    block2 = eng.alloc_slots(n_e * C)
+    slots2 = np.arange(block2.base, block2.base + n_e * C, dtype=np.int32)
+    d = np.array([tree[e] * rates[k] for k in range(C) for e in ekeys])
+    if model == "GTR":
+        eng.queue_build(_lib.CB_MODEL_GTR_EIG, pi, 0.0, gtr_eigensystem(pi, er), slots2, d)
+    elif model == "F81":
+        eng.queue_build(_lib.CB_MODEL_F81, pi, beta, None, slots2, d)
+    else:
+        eng.queue_build(_lib.CB_MODEL_JC, pi, beta, None, slots2, d)
+    built = eng.download_pmats(slots2)
+    ref = np.stack([tm[k][e] for k in range(C) for e in ekeys])
+    if model == "GTR":
+        np.testing.assert_allclose(built, ref, rtol=2e-9, atol=1e-14)
+    else:
+        np.testing.assert_allclose(built, ref, rtol=1e-15, atol=2.3e-16)  # device exp: <= 1 ulp of x (abs)
+        # with x = exp(-beta d) from the host libm the closed forms are bit-identical
+        import math
+        x = np.array([math.exp(-beta * v) for v in d.tolist()])
+        eng.queue_build(_lib.CB_MODEL_F81 if model == "F81" else _lib.CB_MODEL_JC, pi, beta, None, slots2, d, x)
+        assert np.array_equal(eng.download_pmats(slots2), ref)
+    pslots2 = pslots - block.base + block2.base
+    lnl2, _ = eng.eval(None, plan.nodes, plan.children, pslots2, pi, want_snapshot=False)
+    assert abs(lnl2 - want) <= (1e-9 if model == "GTR" else 1e-12) * abs(want)
+    # (c) dirty paths: chain walk == level schedule == full recompute, bit for bit
+    parents = oracle.parent_of(tree)
+    for tip in (1, n_taxa // 2, n_taxa):
+        path = oracle.path_to_root(parents, tip, root)
+        todo = sorted(path, key=plan.index.__getitem__)
+        nodes = np.array(todo, dtype=np.int32)
+        ch = np.array([c for n in todo for c in plan.kids[n]], dtype=np.int32)
+        ps = np.array([[slot_of[k, (n, c)] for k in range(C)] for n in todo for c in plan.kids[n]], dtype=np.int32)
+        l_chain, s1 = eng.eval(snap, nodes, ch, ps, pi, want_snapshot=True)
+        l_levels, s2 = eng.eval(snap, nodes, ch, ps, pi, want_snapshot=True, force_levels=True)
+        l_nosnap, _ = eng.eval(snap, nodes, ch, ps, pi, want_snapshot=False)
+        assert l_chain == lnl and l_levels == lnl and l_nosnap == lnl
+        for n in todo[:-1]:
+            assert np.array_equal(eng.read_partial(s1, n), eng.read_partial(s2, n))
+        eng.release_snapshot(s1)
+        eng.release_snapshot(s2)
+    # (d) batch of candidate paths in one launch == one by one
+    cands, offs, nn, cc, pp = [], [0], [], [], []
+    for tip in range(1, n_taxa + 1):
+        path = sorted(oracle.path_to_root(parents, tip, root), key=plan.index.__getitem__)
+        nn += path
+        cc += [c for n in path for c in plan.kids[n]]
+        # candidate: the tip's edge takes the matrix of another edge (a different likelihood)
+        other = ekeys[(tip * 7) % n_e]
+        for n in path:
+            for c in plan.kids[n]:
+                pp.append([slot_of[k, other if c == tip else (n, c)] for k in range(C)])
+        offs.append(len(nn))
+    nn, cc, pp = np.array(nn, dtype=np.int32), np.array(cc, dtype=np.int32), np.array(pp, dtype=np.int32)
+    got = eng.eval_batch(snap, np.array(offs, dtype=np.int32), nn, cc, pp, pi)
+    for b in range(n_taxa):
+        lo, hi = offs[b], offs[b + 1]
+        one, _ = eng.eval(snap, nn[lo:hi], cc[2 * lo:2 * hi], pp[2 * lo:2 * hi], pi, want_snapshot=False)
+        assert got[b] == one
+    eng.close()
+
+
+def test_deep_tree_needs_scaling(gpu_backend):
+    """A 1300-taxon caterpillar with long branches underflows the reference (lnL = -inf);
+    the GPU path rescales per site and must match the scaled oracle."""
+    from cybayes_b200.engine import Engine
+    from cybayes_b200.likelihood import _Plan
+    n_taxa, n_sites, S, C = 1300, 130, 2, 4
+    rng = np.random.default_rng(7)
+    tree, prev, nxt = {}, 1, n_taxa + 1
+    for tip in range(2, n_taxa + 1):
+        tree[nxt, prev] = float(rng.exponential(0.5))
+        tree[nxt, tip] = float(rng.exponential(0.5))
+        prev, nxt = nxt, nxt + 1
+    root = nxt - 1
+    codes = rng.integers(0, 2, size=(n_taxa, n_sites)).astype(np.uint8)
+    pi = np.array([0.3, 0.7])
+    rates = oracle.site_rates(0.5)
+    # iterative edge order (the recursive restatement would hit the recursion limit here)
+    kids = oracle.children_of(tree)
+    order, stack = [], [root]
+    while stack:
+        nd = stack.pop()
+        x, y = kids[nd]
+        order += [(nd, x), (nd, y)]
+        if y > n_taxa:
+            stack.append(y)
+        if x > n_taxa:
+            stack.append(x)
+    edges = order[::-1]
+    tm = [oracle.prob_t("F81", True, pi, tree, None, r) for r in rates]
+    leaves = _oracle_leaves(codes, S, np.ones((1, S)))
+    unscaled = oracle.mat_ml(pi, root, leaves, edges, tm, n_sites, n_taxa)[0]
+    assert unscaled == -np.inf
+    want = oracle.mat_ml_scaled(pi, root, leaves, edges, tm, n_sites, n_taxa)
+    eng = Engine(codes, S, C)
+    plan = _Plan(edges)
+    ekeys = list(tree.keys())
+    block = eng.alloc_slots(len(ekeys) * C)
+    slot_of = {(k, e): block.base + k * len(ekeys) + i for k in range(C) for i, e in enumerate(ekeys)}
+    eng.upload_pmats(np.arange(block.base, block.base + block.n, dtype=np.int32),
+                     np.stack([tm[k][e] for k in range(C) for e in ekeys]))
+    pslots = np.array([[slot_of[k, e] for k in range(C)] for e in plan.edge_keys], dtype=np.int32)
+    lnl, snap = eng.eval(None, plan.nodes, plan.children, pslots, pi)
+    assert np.isfinite(lnl) and abs(lnl - want) <= 1e-12 * abs(want), (lnl, want)
+    # the deepest dirty path (1299 nodes > the single-launch limit) falls back to levels: same bits
+    parents = oracle.parent_of(tree)
+    path = sorted(oracle.path_to_root(parents, 1, root), key=plan.index.__getitem__)
+    nodes = np.array(path, dtype=np.int32)
+    ch = np.array([c for n in path for c in plan.kids[n]], dtype=np.int32)
+    ps = np.array([[slot_of[k, (n, c)] for k in range(C)] for n in path for c in plan.kids[n]], dtype=np.int32)
+    l2, _ = eng.eval(snap, nodes, ch, ps, pi, want_snapshot=False)
+    assert l2 == lnl
+    short = path[-100:]
+    nodes = np.array(short, dtype=np.int32)
+    ch = np.array([c for n in short for c in plan.kids[n]], dtype=np.int32)
+    ps = np.array([[slot_of[k, (n, c)] for k in range(C)] for n in short for c in plan.kids[n]], dtype=np.int32)
+    l3, _ = eng.eval(snap, nodes, ch, ps, pi, want_snapshot=False)
+    assert l3 == lnl
+    eng.close()
+
+
+TRACES = [("binary_F81", 300), ("twoStates_F81", 300), ("twoStates_JC", 300), ("narrow_F81", 3000),
+          ("narrow_JC", 500), ("broad_F81", 300), ("phon_ringe_JC", 500), ("phon_ringe_F81", 500),
+          ("phon_ringe_GTR", 300), ("ie42_JC", 200), ("ie42_GTR", 60)]
+
+
+def _compare_trace(rec, rows, meta, init_lnl, rel):
+    assert abs(init_lnl - meta["init_lnL"]) <= rel * abs(meta["init_lnL"])
+    assert len(rec) == len(rows)
+    for r, g in zip(rec, rows):
+        i, cur, prop, param, move = r[:5]
+        margin = f"first divergent generation {i}: got {r}, reference {g}"
+        assert str(param) == g["param"] and move == g["move"], margin
+        want = float(g["proposed_ll"])
+        if np.isfinite(want):
+            assert abs(prop - want) <= rel * abs(want), margin
+        assert abs(cur - float(g["current_ll"])) <= rel * abs(float(g["current_ll"])), margin
+
+
+@pytest.mark.parametrize("name,n_gen", TRACES)
+def test_driver_trace_matches_reference(name, n_gen, golden_cases, gpu_backend, tmp_path):
+    """Identical accept/reject trace for a fixed seed: the restated driver on the CUDA engine vs the
+    per-generation output recorded from the unmodified reference driver."""
+    from cybayes_b200.driver import run_chain
+    case = golden_cases[name]
+    rows, meta = load_trace(name)
+    rec = []
+    res = run_chain(golden_io.data_path(case), case["model"], n_gen, 1, case["dtype"], str(tmp_path / "run"),
+                    out=io.StringIO(), fast_spr=False,
+                    on_generation=lambda i, cur, prop, p, mv, acc, st: rec.append((i, cur, prop, p, mv, acc)))
+    rel = REL_GTR if case["model"] == "GTR" else REL_CLOSED
+    _compare_trace(rec, rows[:n_gen], meta, res["initial_lnL"], rel)
+    log_rows = open(str(tmp_path / "run.log")).read().splitlines()[1:]
+    for lr, g in zip(log_rows, rows):
+        f = lr.split("\t")
+        assert f[2] == g["log_TL"] and f[3] == g["alpha"]   # tree length and alpha: exact strings
+    trees = open(str(tmp_path / "run.trees")).read().strip().splitlines()
+    assert trees[-1].split("\t")[1] == meta["last_tree"]     # final sampled tree: exact Newick string
+    counters = sorted(f"({str(k[0])!r}, {k[1]!r}) {res['accepts'].get(k, 0)} {v}" for k, v in res["moves"].items())
+    assert counters == sorted(c.replace("np.str_(", "").replace("'),", "',", 1) for c in meta["counters"])
+
+
+def test_fast_spr_same_trace(golden_cases, gpu_backend, tmp_path):
+    """Dirty-path scoring of external SPR proposals gives the same chain as the full passes."""
+    from cybayes_b200.driver import run_chain
+    case = golden_cases["narrow_F81"]
+    rows, meta = load_trace("narrow_F81")
+    rec = []
+    res = run_chain(golden_io.data_path(case), "F81", 1500, 1, "bin", str(tmp_path / "run"), out=io.StringIO(),
+                    fast_spr=True, on_generation=lambda i, cur, prop, p, mv, acc, st: rec.append((i, cur, prop, p, mv, acc)))
+    _compare_trace(rec, rows[:1500], meta, res["initial_lnL"], REL_CLOSED)
+
+
+def test_unmodified_reference_driver_runs_on_the_engine(golden_cases, gpu_backend, tmp_path, monkeypatch, capsys):
+    """The reference's own driver script, byte-compiled and unmodified (oracle/_ref), on top of the
+    compat modules: same per-generation output as when it ran on the reference's own modules."""
+    pyc = os.path.join(REPO, "oracle", "_ref", "mat_mcmc_gamma.code")
+    if not os.path.exists(pyc):
+        pytest.skip("oracle/_ref/mat_mcmc_gamma.code not built (oracle/build_ref.sh)")
+    compat = os.path.join(REPO, "cybayes_b200", "compat")
+    monkeypatch.syspath_prepend(compat)
+    for m in ("config", "utils", "mcmc_gamma", "ML_gamma", "mcmc", "ML"):
+        monkeypatch.delitem(sys.modules, m, raising=False)
+    case = golden_cases["narrow_F81"]
+    n_gen = 1000
+    monkeypatch.setattr(sys, "argv", ["mat_mcmc_gamma.py", "-i", golden_io.data_path(case), "-m", "F81", "-n",
+                                      str(n_gen), "-t", "1", "-d", "bin", "-o", str(tmp_path / "ref_run")])
+    runpy.run_path(pyc, run_name="__main__")
+    out = capsys.readouterr().out
+    rows, meta = load_trace("narrow_F81")
+    gens = [l.split("\t") for l in out.splitlines() if l.split("\t")[0].isdigit() and len(l.split("\t")) == 6]
+    assert len(gens) == n_gen
+    for f, g in zip(gens, rows):
+        assert f[4] == g["param"] and f[5] == g["move"], (f, g)
+        assert abs(float(f[2]) - float(g["proposed_ll"])) <= REL_CLOSED * abs(float(g["proposed_ll"])), (f, g)
+        assert f[3] == g["TL"], (f, g)
+    for m in ("config", "utils", "mcmc_gamma", "ML_gamma", "mcmc", "ML"):
+        sys.modules.pop(m, None)
