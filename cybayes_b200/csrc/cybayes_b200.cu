@@ -574,7 +574,9 @@ static LaunchConst make_const(cb_ctx* c) {
   return k;
 }
 
-constexpr int MAX_CHAIN_OPS = 160;  // P staging of the 2-state walk: 160 * 256 B = 40 KB
+constexpr int MAX_CHAIN_OPS = 4096;          // longer dirty paths fall back to the level schedule
+constexpr int64_t WALK_MIN_SITES_S2 = 32768; // below this a site tile cannot fill the GPU: use levels
+constexpr int64_t WALK_MIN_SITES_GENERAL = (int64_t)1 << 62;  // general-S walk not enabled yet
 
 static int general_rows_per_chunk(int S) {
   // rows of the two P matrices staged per pass (multiple of 4, <= 64).  Prefer a footprint
@@ -597,7 +599,7 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
     const int64_t pairs = c->P / 2;
     while (threads > 64 && pairs < (int64_t)threads * c->sm_count * 2) threads >>= 1;  // independent of n_r: fixed reduction order
     dim3 grid((unsigned)((pairs + threads - 1) / threads), (unsigned)n_r);
-    const size_t smem = (size_t)max_ops_in_range * 8 * c->n_cats * sizeof(double);
+    const size_t smem = (size_t)std::min(max_ops_in_range, S2_STAGE_OPS) * 8 * c->n_cats * sizeof(double);
     if (c->n_cats == 4)
       prune_s2_kernel<4><<<grid, threads, smem, c->stream>>>(kk);
     else
@@ -614,6 +616,19 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
 }
 
 // Shared implementation of cb_eval (n_lists = 1) and cb_eval_batch.
+//
+// Schedules (all run the same per-node arithmetic, so results are bit-identical):
+//   CHAIN  a dirty path: one launch, one block range walks the ops, the on-path partial is
+//          carried in registers / shared memory                        (ML_gamma.pyx:99-114)
+//   WALK   a whole (sub)tree on a large alignment: ONE launch; every block walks all ops for
+//          its site tile in depth-first order, heavier subtree first.  The child finished
+//          last is carried on chip, so only nodes with two internal children are ever read
+//          back (about a third of them), and those reads come from this block's own recent
+//          writes (L2) when the lighter sibling subtree is small.
+//   LEVELS one launch per tree level, grid.y = nodes of the level: the latency schedule for
+//          small alignments where a site tile alone cannot fill the GPU.
+enum Schedule { SCHED_CHAIN = 0, SCHED_WALK = 1, SCHED_LEVELS = 2 };
+
 static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* offsets, const int32_t* nodes,
                      const int32_t* children, const int32_t* pslots, const double* pi, int flags,
                      int* snapshot_out, double* lnl_out) {
@@ -632,84 +647,136 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
 
   const Snapshot* sin = snapshot_in >= 0 ? &c->snaps[snapshot_in] : nullptr;
   c->op_of_node.assign(n_nodes, -1);
-  std::vector<int> new_bufs;   // buffers written by this evaluation (node order = op order)
-  std::vector<int> new_nodes;
+  std::vector<int> new_bufs, new_nodes;  // buffers written by this evaluation, and their nodes
+  std::vector<int> tmp_bufs;             // temporaries of an evaluation that keeps no snapshot
   int n_ranges = 0;
   std::vector<std::pair<int, int>> launches;  // [range begin, range end) per launch
   std::vector<int> launch_maxops;
-  bool all_chains = true;
+  bool single_launch = true;
+  std::vector<int>& order = c->order;    // position -> original op index (per list)
+  std::vector<int> pos_of, n_sub, kid_op[2];
+  std::vector<char> read_back;
 
   for (int li = 0; li < n_lists; ++li) {
-    const int b = offsets[li], e = offsets[li + 1];
-    REQUIRE(e > b, "empty op list %d", li);
-    // chain detection: every op after the first consumes the previous op's node through
-    // exactly one child and nothing else produced by this list (a dirty path, ML_gamma.pyx:99-114)
+    const int b = offsets[li], e = offsets[li + 1], n = e - b;
+    REQUIRE(n > 0, "empty op list %d", li);
     for (int i = b; i < e; ++i) {
       const int node = nodes[i];
       REQUIRE(node > N && node < n_nodes, "op %d: node %d is not an internal node", i, node);
       REQUIRE(c->op_of_node[node] < 0, "op %d: node %d is computed twice", i, node);
       c->op_of_node[node] = i;
     }
-    bool chain = !(flags & CB_EVAL_FORCE_LEVELS) && (e - b) <= MAX_CHAIN_OPS;
-    for (int i = b; i < e && chain; ++i) {
-      int n_prev = 0;
+    // producers of the children inside this list (-1: tip or snapshot)
+    kid_op[0].assign(n, -1);
+    kid_op[1].assign(n, -1);
+    for (int i = b; i < e; ++i)
       for (int kx = 0; kx < 2; ++kx) {
         const int ch = children[2 * i + kx];
-        if (ch > N && ch < n_nodes && c->op_of_node[ch] >= b) {
-          if (i > b && c->op_of_node[ch] == i - 1) ++n_prev; else chain = false;
+        REQUIRE((ch >= 1 && ch <= N) || (ch > N && ch < n_nodes), "op %d: bad child id %d", i, ch);
+        if (ch > N && c->op_of_node[ch] >= b) {
+          REQUIRE(c->op_of_node[ch] < i, "op %d: child %d is computed after its parent", i, ch);
+          kid_op[kx][i - b] = c->op_of_node[ch] - b;
         }
       }
-      if (i > b && n_prev != 1) chain = false;
+    // chain: every op after the first consumes exactly the previous op and nothing else of the list
+    bool chain = !(flags & CB_EVAL_FORCE_LEVELS) && n <= MAX_CHAIN_OPS;
+    for (int i = 0; i < n && chain; ++i) {
+      const int a0 = kid_op[0][i], a1 = kid_op[1][i];
+      if (i == 0) chain = (a0 < 0 && a1 < 0);
+      else chain = (a0 == i - 1) != (a1 == i - 1) && (a0 < 0 || a0 == i - 1) && (a1 < 0 || a1 == i - 1);
     }
-    for (int i = b; i < e; ++i) c->op_of_node[nodes[i]] = -1;
-    if (!chain) all_chains = false;
     REQUIRE(chain || n_lists == 1, "cb_eval_batch: candidate %d is not a chain of at most %d ops", li, MAX_CHAIN_OPS);
+    Schedule sched = SCHED_CHAIN;
+    if (!chain) {
+      const bool big = c->P >= (c->family_s2 ? WALK_MIN_SITES_S2 : WALK_MIN_SITES_GENERAL);
+      sched = (big && !(flags & CB_EVAL_FORCE_LEVELS)) ? SCHED_WALK : SCHED_LEVELS;
+    }
 
-    for (int i = b; i < e; ++i) {
-      OpDesc& op = c->h_ops[i];
-      const int node = nodes[i];
-      REQUIRE(node > N && node < n_nodes, "op %d: node %d is not an internal node", i, node);
-      const bool is_root = (i == e - 1);
+    order.resize(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    if (sched == SCHED_WALK) {
+      // subtree sizes in ops (children precede parents in the caller's order)
+      n_sub.assign(n, 1);
+      for (int i = 0; i < n; ++i)
+        for (int kx = 0; kx < 2; ++kx)
+          if (kid_op[kx][i] >= 0) n_sub[i] += n_sub[kid_op[kx][i]];
+      // iterative post-order from the root op, heavier child subtree first
+      std::vector<int> stack, out;
+      std::vector<char> expanded(n, 0);
+      out.reserve(n);
+      stack.push_back(n - 1);
+      while (!stack.empty()) {
+        const int i = stack.back();
+        if (expanded[i]) {
+          stack.pop_back();
+          out.push_back(i);
+          continue;
+        }
+        expanded[i] = 1;
+        int a0 = kid_op[0][i], a1 = kid_op[1][i];
+        if (a0 >= 0 && a1 >= 0 && n_sub[a1] > n_sub[a0]) std::swap(a0, a1);  // a0 = heavier
+        if (a1 >= 0) stack.push_back(a1);  // lighter: visited second (pushed first)
+        if (a0 >= 0) stack.push_back(a0);
+      }
+      if ((int)out.size() == n) order = out; else sched = SCHED_LEVELS;  // ops not under the root
+    }
+    pos_of.assign(n, 0);
+    for (int p = 0; p < n; ++p) pos_of[order[p]] = p;
+    // which ops are read back from memory by a later op (as opposed to carried on chip)?
+    read_back.assign(n, 0);
+    for (int i = 0; i < n; ++i)
+      for (int kx = 0; kx < 2; ++kx) {
+        const int k0 = kid_op[kx][i];
+        if (k0 >= 0 && !(sched != SCHED_LEVELS && pos_of[k0] == pos_of[i] - 1)) read_back[k0] = 1;
+      }
+
+    for (int p = 0; p < n; ++p) {
+      const int i0 = order[p], i = b + i0;
+      OpDesc& op = c->h_ops[b + p];
+      const bool is_root = (i0 == n - 1);
+      REQUIRE(!is_root || p == n - 1, "internal error: root is not last");
       op.is_root = is_root ? 1 : 0;
       op.pad_ = 0;
       op.dst = nullptr;
       op.dst_scale = nullptr;
-      const bool keep = is_root ? (want_snap && store_root) : (want_snap || !chain);
+      const bool keep = is_root ? (want_snap && store_root) : (want_snap || read_back[i0]);
       if (keep) {
         int bi;
         if (buffer_acquire(c, &bi)) return 1;
         op.dst = c->buffers[bi].data;
         op.dst_scale = c->buffers[bi].scale;
-        new_bufs.push_back(bi);
-        new_nodes.push_back(node);
+        if (want_snap) {
+          new_bufs.push_back(bi);
+          new_nodes.push_back(nodes[i]);
+        } else {
+          tmp_bufs.push_back(bi);
+        }
       }
       for (int kx = 0; kx < 2; ++kx) {
         const int ch = children[2 * i + kx];
         op.src[kx] = nullptr;
         op.src_scale[kx] = nullptr;
-        if (ch >= 1 && ch <= N) {
+        if (ch <= N) {
           op.kind[kx] = SRC_TIP;
           op.src[kx] = (const char*)c->d_codes + (size_t)(ch - 1) * c->P * c->code_bytes;
-        } else {
-          REQUIRE(ch > N && ch < n_nodes, "op %d: bad child id %d", i, ch);
-          const int prod = c->op_of_node[ch];
-          if (prod >= b && prod < i) {
-            if (chain && prod == i - 1) {
-              op.kind[kx] = SRC_CARRIED;
-            } else {
-              REQUIRE(c->h_ops[prod].dst, "internal error: producer of node %d has no buffer", ch);
-              op.kind[kx] = SRC_BUFFER;
-              op.src[kx] = c->h_ops[prod].dst;
-              op.src_scale[kx] = c->h_ops[prod].dst_scale;
-            }
+        } else if (kid_op[kx][i0] >= 0) {
+          const int pp = pos_of[kid_op[kx][i0]];
+          if (sched != SCHED_LEVELS && pp == p - 1) {
+            op.kind[kx] = SRC_CARRIED;
           } else {
-            REQUIRE(sin && ch < (int)sin->buf_of_node.size() && sin->buf_of_node[ch] >= 0,
-                    "op %d: child %d is neither recomputed nor in the input snapshot", i, ch);
-            const Buffer& bf = c->buffers[sin->buf_of_node[ch]];
+            const OpDesc& prod = c->h_ops[b + pp];
+            REQUIRE(pp < p && prod.dst, "internal error: producer of node %d has no buffer", ch);
             op.kind[kx] = SRC_BUFFER;
-            op.src[kx] = bf.data;
-            op.src_scale[kx] = bf.scale;
+            op.src[kx] = prod.dst;
+            op.src_scale[kx] = prod.dst_scale;
           }
+        } else {
+          REQUIRE(sin && ch < (int)sin->buf_of_node.size() && sin->buf_of_node[ch] >= 0,
+                  "op %d: child %d is neither recomputed nor in the input snapshot", i, ch);
+          const Buffer& bf = c->buffers[sin->buf_of_node[ch]];
+          op.kind[kx] = SRC_BUFFER;
+          op.src[kx] = bf.data;
+          op.src_scale[kx] = bf.scale;
         }
         for (int q = 0; q < C; ++q) {
           const int sl = pslots[(size_t)(2 * i + kx) * C + q];
@@ -718,37 +785,31 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
         }
         for (int q = C; q < CB_MAX_CATS; ++q) op.pslot[kx][q] = 0;
       }
-      c->op_of_node[node] = i;
     }
 
-    if (chain) {
+    if (sched != SCHED_LEVELS) {
       RangeDesc& r = c->h_ranges[n_ranges++];
       r.begin = b; r.end = e; r.out_index = li; r.pad_ = 0;
     } else {
-      // level schedule: level = 1 + max(level of producing ops of the children)
-      c->level_of_op.assign(e - b, 1);
+      single_launch = false;
+      c->level_of_op.assign(n, 1);
       int max_level = 1;
-      for (int i = b; i < e; ++i) {
+      for (int i = 0; i < n; ++i) {
         int lv = 1;
-        for (int kx = 0; kx < 2; ++kx) {
-          const int ch = children[2 * i + kx];
-          if (ch > N) {
-            const int prod = c->op_of_node[ch];
-            if (prod >= b && prod < i) lv = std::max(lv, c->level_of_op[prod - b] + 1);
-          }
-        }
-        c->level_of_op[i - b] = lv;
+        for (int kx = 0; kx < 2; ++kx)
+          if (kid_op[kx][i] >= 0) lv = std::max(lv, c->level_of_op[kid_op[kx][i]] + 1);
+        c->level_of_op[i] = lv;
         max_level = std::max(max_level, lv);
       }
-      c->order.resize(e - b);
-      for (int i = 0; i < e - b; ++i) c->order[i] = i;
-      std::stable_sort(c->order.begin(), c->order.end(),
-                       [&](int a, int bb) { return c->level_of_op[a] < c->level_of_op[bb]; });
+      std::vector<int> by_level(n);
+      for (int i = 0; i < n; ++i) by_level[i] = i;
+      std::stable_sort(by_level.begin(), by_level.end(),
+                       [&](int x, int y) { return c->level_of_op[x] < c->level_of_op[y]; });
       int pos = 0;
       for (int lv = 1; lv <= max_level; ++lv) {
         const int start = n_ranges;
-        while (pos < e - b && c->level_of_op[c->order[pos]] == lv) {
-          const int i = b + c->order[pos++];
+        while (pos < n && c->level_of_op[by_level[pos]] == lv) {
+          const int i = b + by_level[pos++];
           RangeDesc& r = c->h_ranges[n_ranges++];
           r.begin = i; r.end = i + 1; r.out_index = (i == e - 1) ? li : -1; r.pad_ = 0;
         }
@@ -760,7 +821,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     }
     for (int i = b; i < e; ++i) c->op_of_node[nodes[i]] = -1;
   }
-  if (all_chains) {
+  if (single_launch) {
     int mx = 0;
     for (int li = 0; li < n_lists; ++li) mx = std::max(mx, offsets[li + 1] - offsets[li]);
     launches.push_back({0, n_ranges});
@@ -796,6 +857,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   c->last_n_out = n_lists;
 
   // bookkeeping (stream-ordered: temporaries may be recycled by later launches on this stream)
+  for (int bi : tmp_bufs) buffer_release(c, bi);
   if (want_snap) {
     int sid;
     if (!c->free_snaps.empty()) {
@@ -817,9 +879,8 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
       else if (bi <= -2) bi = new_bufs[-2 - bi];  // ownership moves from this evaluation to the snapshot
     }
     if (snapshot_out) *snapshot_out = sid;
-  } else {
-    for (int bi : new_bufs) buffer_release(c, bi);
-    if (snapshot_out) *snapshot_out = -1;
+  } else if (snapshot_out) {
+    *snapshot_out = -1;
   }
 
   if (!(flags & CB_EVAL_NO_SYNC)) {

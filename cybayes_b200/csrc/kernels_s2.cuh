@@ -75,6 +75,8 @@ __device__ __forceinline__ void block_reduce_to_result(double v, const LaunchCon
   }
 }
 
+constexpr int S2_STAGE_OPS = 64;  // P matrices of this many ops are staged in shared memory at a time
+
 template <int C>
 __global__ void __launch_bounds__(256) prune_s2_kernel(const LaunchConst k) {
   extern __shared__ double2 p_stage[];  // [ops in range][2 children][C][2 rows] as (Pi0, Pi1)
@@ -83,23 +85,30 @@ __global__ void __launch_bounds__(256) prune_s2_kernel(const LaunchConst k) {
 
   const RangeDesc rg = k.ranges[blockIdx.y];
   const int nops = rg.end - rg.begin;
-  {
-    double* ps = reinterpret_cast<double*>(p_stage);
-    for (int idx = threadIdx.x; idx < nops * 8 * C; idx += blockDim.x) {
-      const int e = idx & 3, c = (idx >> 2) % C, ch = (idx / (4 * C)) & 1, o = idx / (8 * C);
-      ps[idx] = __ldg(k.pmats + (int64_t)k.ops[rg.begin + o].pslot[ch][c] * 4 + e);
-    }
-  }
-  __syncthreads();
-
   const int64_t P = k.n_sites;
   const int64_t site = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const bool active = site < P;
   double lnl = 0.0;
-  if (site < P) {
-    double2 cur[C][2];  // carried partial: [category][state] x two sites
-    int cur_e0 = 0, cur_e1 = 0;
+  double2 cur[C][2];  // carried partial: [category][state] x two sites
+  int cur_e0 = 0, cur_e1 = 0;
+#pragma unroll
+  for (int c = 0; c < C; ++c) cur[c][0] = cur[c][1] = make_double2(0.0, 0.0);
+
 #pragma unroll 1
-    for (int o = 0; o < nops; ++o) {
+  for (int o0 = 0; o0 < nops; o0 += S2_STAGE_OPS) {
+    const int o1 = min(nops, o0 + S2_STAGE_OPS);
+    if (o0 > 0) __syncthreads();  // everybody is done with the previous chunk's matrices
+    {
+      double* ps = reinterpret_cast<double*>(p_stage);
+      for (int idx = threadIdx.x; idx < (o1 - o0) * 8 * C; idx += blockDim.x) {
+        const int e = idx & 3, c = (idx >> 2) % C, ch = (idx / (4 * C)) & 1, o = idx / (8 * C);
+        ps[idx] = __ldg(k.pmats + (int64_t)k.ops[rg.begin + o0 + o].pslot[ch][c] * 4 + e);
+      }
+    }
+    __syncthreads();
+    if (!active) continue;
+#pragma unroll 1
+    for (int o = o0; o < o1; ++o) {
       const OpDesc* __restrict__ op = k.ops + rg.begin + o;
       double2 out[C][2];
       int e0 = 0, e1 = 0;
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(256) prune_s2_kernel(const LaunchConst k) {
 #pragma unroll
           for (int c = 0; c < C; ++c) { L[c][0] = t0; L[c][1] = t1; }
         }
-        const double2* pm = p_stage + (o * 2 + ch) * C * 2;
+        const double2* pm = p_stage + ((o - o0) * 2 + ch) * C * 2;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
 #pragma unroll

@@ -1,0 +1,249 @@
+"""CPU: host logic of the product (readers, leaf encoding, pattern compression, traversal
+indexing, start state, proposals' random-number consumption, P-table bookkeeping, op-list
+planning, the drivers) with the oracle-backed FakeEngine standing in for the CUDA engine."""
+import hashlib
+import io
+import os
+import random
+import runpy
+import sys
+
+import numpy as np
+import pytest
+
+import golden_io
+import pruning_oracle as oracle
+from conftest import REPO, load_trace
+
+CASES = ["binary_F81", "twoStates_F81", "twoStates_JC", "narrow_F81", "narrow_JC", "narrow_GTR", "broad_F81",
+         "phon_ringe_JC", "phon_ringe_F81", "phon_ringe_GTR", "ie42_JC", "ie42_GTR", "ielex2016_JC",
+         "ielex_multistate_F81", "german_multistate_JC"]
+
+
+def _digest(ll, n_taxa):
+    h = hashlib.sha256()
+    for k in range(1, n_taxa + 1):
+        h.update(np.packbits(np.ascontiguousarray(ll[k]).astype(bool), axis=None).tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_readers_bit_exact(name, golden_cases):
+    from cybayes_b200 import utils
+    case = golden_cases[name]
+    n, S, alphabet, site_dict, ll, taxa, n_sites = getattr(utils, case["reader"])(golden_io.data_path(case))
+    assert (n, S, n_sites) == (case["n_taxa"], case["n_chars"], case["n_sites"])
+    assert alphabet == case["alphabet"] and taxa == case["taxa"]
+    assert _digest(ll, n) == case["leaf_digest"]            # 0/1 leaf matrices, bit for bit
+    assert ll[1].shape == (S, n_sites) and ll[1].flags["C_CONTIGUOUS"] and ll[1].dtype == np.float64
+    assert sorted(ll.keys()) == list(range(1, n + 1)) and len(ll) == n
+
+
+def test_read_multi_phy_accepts_readphy_layout_and_rejects_garbage(golden_cases, tmp_path):
+    from cybayes_b200 import utils
+    case = golden_cases["ielex_multistate_F81"]
+    a = utils.readMultiPhy(golden_io.data_path(case))     # the reference raises here
+    b = utils.readPhy(golden_io.data_path(case))
+    assert a[2] == b[2] and np.array_equal(a[4].codes, b[4].codes)
+    bad = tmp_path / "bad.phy"
+    bad.write_text("2 3\nt1 0 1 0\nt2 011\n")
+    with pytest.raises(ValueError, match="too many values to unpack"):
+        utils.readBinaryPhy(str(bad))
+    ragged = tmp_path / "ragged.phy"
+    ragged.write_text("2 3\nt1 010\n\nt2 01\n")
+    with pytest.raises((AssertionError, ValueError)):
+        utils.readBinaryPhy(str(ragged))
+
+
+def test_polymorphic_and_missing_cells(tmp_path):
+    from cybayes_b200 import utils
+    f = tmp_path / "poly.phy"
+    f.write_text("3 4\nA\tx y x/y ?\nB\ty z - x/z\nC\tz/y x y z\n")
+    n, S, alphabet, _, ll, taxa, n_sites = utils.readPhy(str(f))
+    _, S2, alphabet2, _, ll2, _, _ = oracle.read_phylip(str(f), "readPhy")
+    assert alphabet == alphabet2 == ["x", "y", "z"]
+    for k in (1, 2, 3):
+        assert np.array_equal(ll[k], ll2[k])
+    assert ll.codes.dtype == np.uint8 and ll.codes.max() >= S   # ambiguity codes in use
+
+
+def _py_patterns(codes):
+    seen, weights, smap = {}, [], []
+    for p in range(codes.shape[1]):
+        key = codes[:, p].tobytes()
+        if key not in seen:
+            seen[key] = len(weights)
+            weights.append(0)
+        weights[seen[key]] += 1
+        smap.append(seen[key])
+    cols = [np.frombuffer(k, dtype=codes.dtype) for k in seen]
+    return np.array(cols).T, np.array(weights, dtype=float), np.array(smap)
+
+
+@pytest.mark.parametrize("name,n_patterns", [("narrow_F81", 943), ("broad_F81", 4377), ("binary_F81", None)])
+def test_pattern_compression_bit_exact(name, n_patterns, golden_cases):
+    from cybayes_b200 import utils
+    from cybayes_b200.alignment import compress_patterns
+    case = golden_cases[name]
+    codes = getattr(utils, case["reader"])(golden_io.data_path(case))[4].codes
+    pat, w, smap = compress_patterns(codes)
+    pat2, w2, smap2 = _py_patterns(codes)
+    assert np.array_equal(pat, pat2) and np.array_equal(w, w2) and np.array_equal(smap, smap2)
+    assert w.sum() == codes.shape[1] and np.array_equal(pat[:, smap], codes)
+    if n_patterns:
+        assert pat.shape[1] == n_patterns      # 943 of 2351, 4377 of 5695
+
+
+@pytest.mark.parametrize("name", ["binary_F81", "narrow_F81", "narrow_JC", "phon_ringe_GTR", "ie42_JC"])
+def test_state_init_consumes_random_numbers_like_the_reference(name, golden_cases, fake_backend):
+    from cybayes_b200 import config
+    from cybayes_b200.driver import load_alignment
+    from cybayes_b200.mcmc_gamma import get_siterates, state_init
+    case = golden_cases[name]
+    np.random.seed(1234)
+    random.seed(1234)
+    load_alignment(golden_io.data_path(case), case["dtype"], case["reader"])
+    config.MODEL = case["model"]
+    st = state_init()
+    assert [[p, c, t] for (p, c), t in st["tree"].items()] == case["tree"]    # dict order and lengths
+    assert st["root"] == case["root"] and st["srates"] == case["srates"]
+    assert [list(e) for e in st["postorder"]] == case["postorder"]
+    assert np.array_equal(np.asarray(st["pi"]), case["pi"])
+    assert hashlib.sha256(np.asarray(st["rates"]).tobytes()).hexdigest() == case["rates_digest"]
+    assert get_siterates(st["srates"]) == case["site_rates"]
+    assert config.NORM_BETA == case["norm_beta"]
+
+
+def _run_trace(name, n_gen, golden_cases, tmp_path, **kw):
+    from cybayes_b200.driver import run_chain
+    case = golden_cases[name]
+    rec = []
+    res = run_chain(golden_io.data_path(case), case["model"], n_gen, 1, case["dtype"], str(tmp_path / "run"),
+                    out=io.StringIO(), on_generation=lambda i, cur, prop, p, mv, acc, st: rec.append(
+                        (i, cur, prop, str(p), mv, acc)), **kw)
+    return rec, res
+
+
+@pytest.mark.parametrize("name,n_gen", [("binary_F81", 300), ("twoStates_JC", 300), ("narrow_F81", 250),
+                                        ("phon_ringe_F81", 300), ("phon_ringe_GTR", 150)])
+def test_driver_trace_on_fake_engine(name, n_gen, golden_cases, fake_backend, tmp_path):
+    """Move sequence, proposed likelihoods and accept decisions equal the reference's recorded run."""
+    rows, meta = load_trace(name)
+    rec, res = _run_trace(name, n_gen, golden_cases, tmp_path)
+    assert abs(res["initial_lnL"] - meta["init_lnL"]) <= 1e-12 * abs(meta["init_lnL"])
+    for r, g in zip(rec, rows):
+        assert (r[3], r[4]) == (g["param"], g["move"]), (r, g)
+        assert abs(r[2] - float(g["proposed_ll"])) <= 1e-10 * abs(float(g["proposed_ll"])), (r, g)
+        assert abs(r[1] - float(g["current_ll"])) <= 1e-10 * abs(float(g["current_ll"])), (r, g)
+    log_rows = open(str(tmp_path / "run.log")).read().splitlines()[1:]
+    assert [l.split("\t")[2:] for l in log_rows] == [[g["log_TL"], g["alpha"]] for g in rows[:n_gen]]
+
+
+def test_fast_spr_is_the_same_chain(golden_cases, fake_backend, tmp_path):
+    rec_a, _ = _run_trace("binary_F81", 300, golden_cases, tmp_path, fast_spr=False)
+    n_ops_full = sum(e.n_ops for e in fake_backend.instances)
+    fake_backend.instances.clear()
+    from cybayes_b200 import likelihood
+    likelihood.reset_engines()
+    rec_b, _ = _run_trace("binary_F81", 300, golden_cases, tmp_path, fast_spr=True)
+    n_ops_fast = sum(e.n_ops for e in fake_backend.instances)
+    assert [(r[3], r[4], r[5]) for r in rec_a] == [(r[3], r[4], r[5]) for r in rec_b]
+    assert all(abs(a[2] - b[2]) <= 1e-12 * abs(a[2]) for a, b in zip(rec_a, rec_b))
+    assert n_ops_fast < n_ops_full
+
+
+def test_unmodified_reference_driver_on_compat_modules(golden_cases, fake_backend, tmp_path, monkeypatch, capsys):
+    """The reference's own script (byte-compiled, unmodified) imports `utils`, `config`, `mcmc_gamma`,
+    `ML_gamma` from cybayes_b200/compat and produces its recorded per-generation output."""
+    script = os.path.join(REPO, "oracle", "_ref", "mat_mcmc_gamma.code")
+    if not os.path.exists(script):
+        script = "/root/reference/mat_mcmc_gamma.py"
+    if not os.path.exists(script):
+        pytest.skip("no reference driver available")
+    monkeypatch.syspath_prepend(os.path.join(REPO, "cybayes_b200", "compat"))
+    names = ("config", "utils", "mcmc_gamma", "ML_gamma", "mcmc", "ML")
+    for m in names:
+        monkeypatch.delitem(sys.modules, m, raising=False)
+    case = golden_cases["narrow_F81"]
+    n_gen = 200
+    monkeypatch.setattr(sys, "argv", ["mat_mcmc_gamma.py", "-i", golden_io.data_path(case), "-m", "F81", "-n",
+                                      str(n_gen), "-t", "1", "-d", "bin", "-o", str(tmp_path / "ref_run")])
+    runpy.run_path(script, run_name="__main__")
+    out = capsys.readouterr().out
+    rows, _ = load_trace("narrow_F81")
+    gens = [l.split("\t") for l in out.splitlines() if l.split("\t")[0].isdigit() and len(l.split("\t")) == 6]
+    assert len(gens) == n_gen
+    for f, g in zip(gens, rows):
+        assert (f[4], f[5], f[3]) == (g["param"], g["move"], g["TL"]), (f, g)
+        assert abs(float(f[2]) - float(g["proposed_ll"])) <= 1e-10 * abs(float(g["proposed_ll"]))
+    for m in names:
+        sys.modules.pop(m, None)
+
+
+def test_pmat_table_lifetimes(fake_backend):
+    """NNI aliasing: one slot referenced from two edges must survive deleting either key."""
+    from cybayes_b200.subst import PMatTable, host_matrix
+    eng = fake_backend(np.zeros((4, 8), dtype=np.uint8), 2, 4)
+    block = eng.alloc_slots(3)
+    t = PMatTable(eng, [(5, 1), (5, 2), (6, 5)], block)
+    extra = host_matrix(eng, np.eye(2) * 0.5)
+    slot = extra.slot
+    t[5, 1] = extra
+    t[6, 3] = t[5, 1].copy()
+    del extra
+    del t[5, 1]
+    assert t._slots[6, 3] == slot and slot not in eng._free_slots.get(1, [])
+    del t[6, 3]
+    assert slot in eng._free_slots.get(1, [])          # last reference gone -> slot back in the pool
+    assert (5, 2) in t and len(t) == 2 and list(t.keys()) == [(5, 2), (6, 5)]
+    t2 = t.copy()
+    del t
+    assert block.base not in eng._free_slots.get(3, [])   # the copy keeps the block alive
+    del t2, block
+    assert eng._free_slots.get(3) is not None
+
+
+def test_plan_orders_ops_like_the_reference_walk(golden_cases):
+    from cybayes_b200.likelihood import _Plan
+    case = golden_cases["binary_F81"]
+    edges = [tuple(e) for e in case["postorder"]]
+    plan = _Plan(edges)
+    done, seen = [], {}
+    for p, c in edges:                      # ML_gamma.pyx:24-36: a parent completes at its 2nd edge
+        seen[p] = seen.get(p, 0) + 1
+        if seen[p] == 2:
+            done.append(p)
+    assert plan.nodes.tolist() == done and plan.nodes[-1] == case["root"]
+    for i, n in enumerate(plan.nodes.tolist()):
+        assert tuple(plan.children[2 * i:2 * i + 2]) == plan.kids[n]
+        for c in plan.kids[n]:
+            assert c <= case["n_taxa"] or plan.index[c] < i      # children before parents
+
+
+def test_non_gamma_surface(golden_cases, fake_backend):
+    """mcmc / ML mirrors (single rate category): state_init + matML + cache_matML vs the oracle."""
+    from cybayes_b200 import ML, config, mcmc
+    from cybayes_b200.driver import load_alignment
+    case = golden_cases["phon_ringe_F81"]
+    np.random.seed(1234)
+    random.seed(1234)
+    load_alignment(golden_io.data_path(case), "multi")
+    config.MODEL = "F81"
+    st = mcmc.state_init()
+    lnl, cache = ML.matML(st, config.TAXA, config.LEAF_LLMAT)
+    _, _, _, _, ll, _, n_sites = oracle.read_phylip(golden_io.data_path(case), "readMultiPhy")
+    tm = [oracle.prob_t("F81", False, np.asarray(st["pi"]), st["tree"], None, 1.0)]
+    part = {}
+    for p, c in st["postorder"]:
+        v = tm[0][p, c].dot(ll[c] if c <= config.N_TAXA else part[c])
+        part[p] = v if p not in part else part[p] * v
+    want = np.sum(np.log(np.dot(np.asarray(st["pi"]), part[st["root"]])))       # ML.pyx:48
+    assert abs(lnl - want) <= 1e-12 * abs(want)
+    tree2, hr, pr, edge = mcmc.scale_edge(st["tree"].copy())
+    st2 = dict(st, tree=tree2)
+    st2["transitionMat"] = mcmc.get_edge_transition_mat(st["pi"], st["rates"], tree2[edge], st["transitionMat"], edge)
+    path = mcmc.get_path2root(mcmc.adjlist2reverse_nodes_dict(st["tree"]), edge[1], st["root"])
+    l2, _ = ML.cache_matML(st2, config.TAXA, config.LEAF_LLMAT, cache, path)
+    tm2 = [oracle.prob_t("F81", False, np.asarray(st["pi"]), tree2, None, 1.0)]
+    want2 = oracle.mat_ml(np.asarray(st["pi"]), st["root"], ll, st["postorder"], tm2 * 1, n_sites, config.N_TAXA, 1)[0]
+    assert abs(l2 - want2) <= 1e-12 * abs(want2)
