@@ -11,6 +11,7 @@
 #include <limits.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -96,6 +97,8 @@ struct cb_ctx {
   int n_taxa = 0, n_states = 0, n_cats = 0, code_bytes = 1, n_amb = 0;
   int64_t n_sites = 0, P = 0;  // real and padded pattern counts
   bool family_s2 = false;
+  int s2_vec = 1;  // sites per thread of the 2-state kernel on large alignments
+  int s2_minb = 3; // its __launch_bounds__ min blocks per SM (experiment knob)
   void* d_codes = nullptr;
   double* d_weights = nullptr;
   double* d_amb = nullptr;
@@ -180,6 +183,8 @@ extern "C" int cb_create(int device, cb_ctx** out) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
+  if (const char* v = getenv("CYBAYES_S2_V")) c->s2_vec = (atoi(v) == 2) ? 2 : 1;
+  if (const char* v = getenv("CYBAYES_S2_MINB")) c->s2_minb = (atoi(v) == 4) ? 4 : 3;
   CU(cudaFuncSetAttribute(prune_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = c;
   return 0;
@@ -595,15 +600,24 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
   LaunchConst kk = k;
   kk.ranges = k.ranges + r_begin;
   if (c->family_s2) {
-    int threads = 256;
-    const int64_t pairs = c->P / 2;
-    while (threads > 64 && pairs < (int64_t)threads * c->sm_count * 2) threads >>= 1;  // independent of n_r: fixed reduction order
-    dim3 grid((unsigned)((pairs + threads - 1) / threads), (unsigned)n_r);
-    const size_t smem = (size_t)std::min(max_ops_in_range, S2_STAGE_OPS) * 8 * c->n_cats * sizeof(double);
-    if (c->n_cats == 4)
-      prune_s2_kernel<4><<<grid, threads, smem, c->stream>>>(kk);
-    else
-      prune_s2_kernel<1><<<grid, threads, smem, c->stream>>>(kk);
+    // Fixed per alignment (independent of the schedule) so the reduction order never changes:
+    // big alignments: 256 threads x V sites (V from CYBAYES_S2_V, default 1 = more resident warps);
+    // small alignments: 64-thread blocks, one site per thread, to spread over the SMs.
+    const size_t smem = s2_smem_bytes(max_ops_in_range, c->n_cats);
+    const bool small = c->P < (int64_t)64 * 2 * c->sm_count * 4;
+    const int V = small ? 1 : c->s2_vec;
+    const int threads = small ? 64 : 256;
+    dim3 grid((unsigned)((c->P + (int64_t)threads * V - 1) / ((int64_t)threads * V)), (unsigned)n_r);
+#define CB_LAUNCH_S2(CC, VV, TT, MB) prune_s2_kernel<CC, VV, TT, MB><<<grid, TT, smem, c->stream>>>(kk)
+    if (c->n_cats == 4) {
+      if (small) CB_LAUNCH_S2(4, 1, 64, 8);
+      else if (V == 1 && c->s2_minb == 4) CB_LAUNCH_S2(4, 1, 256, 4);
+      else if (V == 1) CB_LAUNCH_S2(4, 1, 256, 3);
+      else CB_LAUNCH_S2(4, 2, 256, 2);
+    } else {
+      if (small) CB_LAUNCH_S2(1, 1, 64, 8); else if (V == 1) CB_LAUNCH_S2(1, 1, 256, 4); else CB_LAUNCH_S2(1, 2, 256, 4);
+    }
+#undef CB_LAUNCH_S2
   } else {
     const int R = general_rows_per_chunk(c->n_states);
     REQUIRE(R > 0, "n_states = %d does not fit the shared-memory tiling", c->n_states);

@@ -75,148 +75,242 @@ __device__ __forceinline__ void block_reduce_to_result(double v, const LaunchCon
   }
 }
 
-constexpr int S2_STAGE_OPS = 64;  // P matrices of this many ops are staged in shared memory at a time
+constexpr int S2_STAGE_OPS = 64;  // ops whose descriptors + P matrices are staged in shared memory at a time
 
-template <int C>
-__global__ void __launch_bounds__(256) prune_s2_kernel(const LaunchConst k) {
-  extern __shared__ double2 p_stage[];  // [ops in range][2 children][C][2 rows] as (Pi0, Pi1)
+// Vector of V doubles / ints per thread (V sites), with 8*V-byte global accesses.
+template <int V> struct VecD;
+template <> struct VecD<1> {
+  double v[1];
+  __device__ __forceinline__ void load(const double* p) { v[0] = __ldcg(p); }
+  __device__ __forceinline__ void store(double* p) const { __stcg(p, v[0]); }
+};
+template <> struct VecD<2> {
+  double v[2];
+  __device__ __forceinline__ void load(const double* p) { const double2 t = ld_cg2(p); v[0] = t.x; v[1] = t.y; }
+  __device__ __forceinline__ void store(double* p) const { st_cg2(p, make_double2(v[0], v[1])); }
+};
+template <int V> __device__ __forceinline__ void load_ints(const int32_t* p, int (&e)[V]);
+template <> __device__ __forceinline__ void load_ints<1>(const int32_t* p, int (&e)[1]) { e[0] = __ldcg(p); }
+template <> __device__ __forceinline__ void load_ints<2>(const int32_t* p, int (&e)[2]) {
+  const int2 t = __ldcg(reinterpret_cast<const int2*>(p)); e[0] = t.x; e[1] = t.y;
+}
+template <int V> __device__ __forceinline__ void store_ints(int32_t* p, const int (&e)[V]);
+template <> __device__ __forceinline__ void store_ints<1>(int32_t* p, const int (&e)[1]) { __stcg(p, e[0]); }
+template <> __device__ __forceinline__ void store_ints<2>(int32_t* p, const int (&e)[2]) {
+  __stcg(reinterpret_cast<int2*>(p), make_int2(e[0], e[1]));
+}
+template <int V> __device__ __forceinline__ void load_codes(const void* row, int code_bytes, int64_t site, unsigned (&c)[V]);
+template <> __device__ __forceinline__ void load_codes<1>(const void* row, int code_bytes, int64_t site, unsigned (&c)[1]) {
+  c[0] = (code_bytes == 1) ? (unsigned)__ldg(static_cast<const uint8_t*>(row) + site)
+                           : (unsigned)__ldg(static_cast<const uint16_t*>(row) + site);
+}
+template <> __device__ __forceinline__ void load_codes<2>(const void* row, int code_bytes, int64_t site, unsigned (&c)[2]) {
+  if (code_bytes == 1) {
+    const uchar2 t = __ldg(reinterpret_cast<const uchar2*>(static_cast<const uint8_t*>(row) + site));
+    c[0] = t.x; c[1] = t.y;
+  } else {
+    const ushort2 t = __ldg(reinterpret_cast<const ushort2*>(static_cast<const uint16_t*>(row) + site));
+    c[0] = t.x; c[1] = t.y;
+  }
+}
+
+// per-op record staged in shared memory (64 B)
+struct S2Stage {
+  double* dst;
+  int32_t* dst_scale;
+  const void* src[2];
+  const int32_t* src_scale[2];
+  int32_t kind[2];
+  int32_t is_root, pad_;
+};
+static_assert(sizeof(S2Stage) == 64, "S2Stage is 64 bytes");
+
+template <int V>
+__device__ __forceinline__ void fetch_codes(const S2Stage& op, int code_bytes, int64_t site, unsigned (&code)[2][V]) {
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch)
+    if (op.kind[ch] == SRC_TIP) load_codes<V>(op.src[ch], code_bytes, site, code[ch]);
+}
+
+__host__ __device__ inline size_t s2_smem_bytes(int ops, int C) {
+  const int n = ops < S2_STAGE_OPS ? ops : S2_STAGE_OPS;
+  return (size_t)n * (sizeof(S2Stage) + (size_t)8 * C * sizeof(double));
+}
+
+template <int C, int V, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchConst k) {
+  extern __shared__ __align__(16) unsigned char s2_smem[];
   __shared__ double red[32];
   __shared__ int last_flag;
 
   const RangeDesc rg = k.ranges[blockIdx.y];
   const int nops = rg.end - rg.begin;
+  const int n_stage = min(nops, S2_STAGE_OPS);
+  S2Stage* st = reinterpret_cast<S2Stage*>(s2_smem);
+  double2* p_stage = reinterpret_cast<double2*>(s2_smem + (size_t)n_stage * sizeof(S2Stage));  // [op][child][C][row] = (Pi0, Pi1)
+
   const int64_t P = k.n_sites;
-  const int64_t site = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int64_t tile0 = (int64_t)blockIdx.x * (THREADS * V);
+  const int64_t site = tile0 + (int64_t)threadIdx.x * V;
   const bool active = site < P;
   double lnl = 0.0;
-  double2 cur[C][2];  // carried partial: [category][state] x two sites
-  int cur_e0 = 0, cur_e1 = 0;
+  VecD<V> cur[C][2];  // carried partial: [category][state] x V sites
+  int cur_e[V];
 #pragma unroll
-  for (int c = 0; c < C; ++c) cur[c][0] = cur[c][1] = make_double2(0.0, 0.0);
+  for (int v = 0; v < V; ++v) cur_e[v] = 0;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int v = 0; v < V; ++v) cur[c][0].v[v] = cur[c][1].v[v] = 0.0;
 
 #pragma unroll 1
   for (int o0 = 0; o0 < nops; o0 += S2_STAGE_OPS) {
     const int o1 = min(nops, o0 + S2_STAGE_OPS);
-    if (o0 > 0) __syncthreads();  // everybody is done with the previous chunk's matrices
+    if (o0 > 0) __syncthreads();  // everybody is done with the previous chunk
+    // stage descriptors (one thread per op) ...
+    for (int o = threadIdx.x; o < o1 - o0; o += THREADS) {
+      const OpDesc* __restrict__ op = k.ops + rg.begin + o0 + o;
+      S2Stage r;
+      r.dst = op->dst; r.dst_scale = op->dst_scale;
+      r.src[0] = op->src[0]; r.src[1] = op->src[1];
+      r.src_scale[0] = op->src_scale[0]; r.src_scale[1] = op->src_scale[1];
+      r.kind[0] = op->kind[0]; r.kind[1] = op->kind[1];
+      r.is_root = op->is_root; r.pad_ = 0;
+      st[o] = r;
+    }
+    // ... their P matrices ...
     {
       double* ps = reinterpret_cast<double*>(p_stage);
-      for (int idx = threadIdx.x; idx < (o1 - o0) * 8 * C; idx += blockDim.x) {
+      for (int idx = threadIdx.x; idx < (o1 - o0) * 8 * C; idx += THREADS) {
         const int e = idx & 3, c = (idx >> 2) % C, ch = (idx / (4 * C)) & 1, o = idx / (8 * C);
         ps[idx] = __ldg(k.pmats + (int64_t)k.ops[rg.begin + o0 + o].pslot[ch][c] * 4 + e);
       }
     }
-    __syncthreads();
-    if (!active) continue;
-#pragma unroll 1
-    for (int o = o0; o < o1; ++o) {
-      const OpDesc* __restrict__ op = k.ops + rg.begin + o;
-      double2 out[C][2];
-      int e0 = 0, e1 = 0;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const int kind = op->kind[ch];
-        double2 L[C][2];
-        if (kind == SRC_CARRIED) {
-#pragma unroll
-          for (int c = 0; c < C; ++c) { L[c][0] = cur[c][0]; L[c][1] = cur[c][1]; }
-          e0 += cur_e0; e1 += cur_e1;
-        } else if (kind == SRC_BUFFER) {
-          const double* src = static_cast<const double*>(op->src[ch]) + site;
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            L[c][0] = ld_cg2(src + (int64_t)(2 * c) * P);
-            L[c][1] = ld_cg2(src + (int64_t)(2 * c + 1) * P);
-          }
-          const int2 se = __ldcg(reinterpret_cast<const int2*>(op->src_scale[ch] + site));
-          e0 += se.x; e1 += se.y;
-        } else {  // tip: state codes -> 0/1 indicator columns (utils.pyx:99-111)
-          unsigned c0, c1;
-          if (k.code_bytes == 1) {
-            const uchar2 cc = __ldg(reinterpret_cast<const uchar2*>(static_cast<const uint8_t*>(op->src[ch]) + site));
-            c0 = cc.x; c1 = cc.y;
-          } else {
-            const ushort2 cc = __ldg(reinterpret_cast<const ushort2*>(static_cast<const uint16_t*>(op->src[ch]) + site));
-            c0 = cc.x; c1 = cc.y;
-          }
-          double2 t0, t1;  // t0 = indicator of state 0 for (site, site+1); t1 = state 1
-          t0.x = (c0 < 2) ? (c0 == 0 ? 1.0 : 0.0) : __ldg(k.amb + (c0 - 2) * 2);
-          t1.x = (c0 < 2) ? (c0 == 1 ? 1.0 : 0.0) : __ldg(k.amb + (c0 - 2) * 2 + 1);
-          t0.y = (c1 < 2) ? (c1 == 0 ? 1.0 : 0.0) : __ldg(k.amb + (c1 - 2) * 2);
-          t1.y = (c1 < 2) ? (c1 == 1 ? 1.0 : 0.0) : __ldg(k.amb + (c1 - 2) * 2 + 1);
-#pragma unroll
-          for (int c = 0; c < C; ++c) { L[c][0] = t0; L[c][1] = t1; }
-        }
-        const double2* pm = p_stage + ((o - o0) * 2 + ch) * C * 2;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const double2 pr = pm[c * 2 + i];  // (P[i][0], P[i][1]) broadcast
-            double2 v;
-            v.x = fma(pr.y, L[c][1].x, pr.x * L[c][0].x);
-            v.y = fma(pr.y, L[c][1].y, pr.x * L[c][0].y);
-            if (ch == 0) {
-              out[c][i] = v;
-            } else {
-              out[c][i].x *= v.x;
-              out[c][i].y *= v.y;
-            }
-          }
+    // ... and pull this tile's tip codes of the NEXT chunk towards L2 while this chunk computes
+    {
+      const int nxt = min(nops, o1 + S2_STAGE_OPS) - o1;
+      const int tile_bytes = THREADS * V * k.code_bytes;
+      const int lines = (tile_bytes + 127) / 128;
+      for (int idx = threadIdx.x; idx < nxt * 2 * lines; idx += THREADS) {
+        const int ln = idx % lines, oc = idx / lines;
+        const OpDesc* __restrict__ op = k.ops + rg.begin + o1 + (oc >> 1);
+        if (op->kind[oc & 1] == SRC_TIP) {
+          const char* a = static_cast<const char*>(op->src[oc & 1]) + tile0 * k.code_bytes + ln * 128;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         }
       }
-      if (!op->is_root) {
-        double m0 = out[0][0].x, m1 = out[0][0].y;
+    }
+    __syncthreads();
+    if (!active) continue;
+    // tip codes are fetched one op ahead (register prefetch): by the time an op starts, its codes
+    // have had a whole op of compute to arrive from L2
+    unsigned code_next[2][V];
+    fetch_codes<V>(st[0], k.code_bytes, site, code_next);
+#pragma unroll 1
+    for (int o = o0; o < o1; ++o) {
+      const S2Stage& op = st[o - o0];
+      unsigned code[2][V];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
+      for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            m0 = fmax(m0, out[c][i].x);
-            m1 = fmax(m1, out[c][i].y);
-          }
-        }
-        const int x0 = exponent_of(m0), x1 = exponent_of(m1);
-        const double f0 = pow2_neg(x0), f1 = pow2_neg(x1);
+        for (int v = 0; v < V; ++v) code[ch][v] = code_next[ch][v];
+      if (o + 1 < o1) fetch_codes<V>(st[o + 1 - o0], k.code_bytes, site, code_next);
+
+      VecD<V> out[C][2];
+      int e_in[V];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
+      for (int v = 0; v < V; ++v) e_in[v] = 0;
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            cur[c][i].x = out[c][i].x * f0;
-            cur[c][i].y = out[c][i].y * f1;
-          }
-        }
-        cur_e0 = e0 + x0;
-        cur_e1 = e1 + x1;
-        if (op->dst != nullptr) {
-          double* dst = op->dst + site;
+      for (int ch = 0; ch < 2; ++ch) {
+        const int kind = op.kind[ch];
+        const double2* pm = p_stage + ((o - o0) * 2 + ch) * C * 2;  // (P[i][0], P[i][1]) broadcasts
+        // v[i] = P[i][0] L[0] + P[i][1] L[1]; first child initialises `out`, second multiplies into it
+#define CB_S2_APPLY(L0, L1)                                                   \
+  _Pragma("unroll") for (int c = 0; c < C; ++c) {                            \
+    _Pragma("unroll") for (int i = 0; i < 2; ++i) {                          \
+      const double2 pr = pm[c * 2 + i];                                       \
+      _Pragma("unroll") for (int v = 0; v < V; ++v) {                        \
+        const double x = fma(pr.y, (L1), pr.x * (L0));                        \
+        if (ch == 0) out[c][i].v[v] = x; else out[c][i].v[v] *= x;            \
+      }                                                                       \
+    }                                                                         \
+  }
+        if (kind == SRC_CARRIED) {
+          CB_S2_APPLY(cur[c][0].v[v], cur[c][1].v[v])
+#pragma unroll
+          for (int v = 0; v < V; ++v) e_in[v] += cur_e[v];
+        } else if (kind == SRC_BUFFER) {
+          const double* src = static_cast<const double*>(op.src[ch]) + site;
+          VecD<V> L[C][2];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            st_cg2(dst + (int64_t)(2 * c) * P, cur[c][0]);
-            st_cg2(dst + (int64_t)(2 * c + 1) * P, cur[c][1]);
+            L[c][0].load(src + (int64_t)(2 * c) * P);
+            L[c][1].load(src + (int64_t)(2 * c + 1) * P);
           }
-          __stcg(reinterpret_cast<int2*>(op->dst_scale + site), make_int2(cur_e0, cur_e1));
+          int se[V];
+          load_ints<V>(op.src_scale[ch] + site, se);
+          CB_S2_APPLY(L[c][0].v[v], L[c][1].v[v])
+#pragma unroll
+          for (int v = 0; v < V; ++v) e_in[v] += se[v];
+        } else {  // tip: state code -> 0/1 indicator column (utils.pyx:99-111); 2 = '?' / '-' / '0/1'
+          double t0[V], t1[V];
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            t0[v] = (code[ch][v] != 1u) ? 1.0 : 0.0;
+            t1[v] = (code[ch][v] != 0u) ? 1.0 : 0.0;
+          }
+          CB_S2_APPLY(t0[v], t1[v])
+        }
+#undef CB_S2_APPLY
+      }
+      if (!op.is_root) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          // all entries are >= 0, so the max of the high words carries the exponent of the max
+          int mh = __double2hiint(out[0][0].v[v]);
+#pragma unroll
+          for (int c = 0; c < C; ++c) mh = max(mh, max(__double2hiint(out[c][0].v[v]), __double2hiint(out[c][1].v[v])));
+          const int be = (mh >> 20) & 0x7ff;
+          const int x = (be == 0 || be == 0x7ff) ? 0 : be - 1023;
+          const double f = pow2_neg(x);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            cur[c][0].v[v] = out[c][0].v[v] * f;
+            cur[c][1].v[v] = out[c][1].v[v] * f;
+          }
+          cur_e[v] = e_in[v] + x;
+        }
+        if (op.dst != nullptr) {
+          double* dst = op.dst + site;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            cur[c][0].store(dst + (int64_t)(2 * c) * P);
+            cur[c][1].store(dst + (int64_t)(2 * c + 1) * P);
+          }
+          store_ints<V>(op.dst_scale + site, cur_e);
         }
       } else {
         // ll_p = sum_c (pi . L_c) / n_cats ; lnL += w_p * log(ll_p)      ML_gamma.pyx:38,40
         const double pi0 = __ldg(k.pi), pi1 = __ldg(k.pi + 1);
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          s0 += fma(pi1, out[c][1].x, pi0 * out[c][0].x) / k.cats;
-          s1 += fma(pi1, out[c][1].y, pi0 * out[c][0].y) / k.cats;
-        }
-        if (op->dst != nullptr) {  // optional store of the (unscaled-at-this-node) root partial
-          double* dst = op->dst + site;
+        if (op.dst != nullptr) {  // optional store of the (unscaled-at-this-node) root partial
+          double* dst = op.dst + site;
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            st_cg2(dst + (int64_t)(2 * c) * P, out[c][0]);
-            st_cg2(dst + (int64_t)(2 * c + 1) * P, out[c][1]);
+            out[c][0].store(dst + (int64_t)(2 * c) * P);
+            out[c][1].store(dst + (int64_t)(2 * c + 1) * P);
           }
-          __stcg(reinterpret_cast<int2*>(op->dst_scale + site), make_int2(e0, e1));
+          store_ints<V>(op.dst_scale + site, e_in);
         }
-        const double2 w = ld_cg2(k.weights + site);
+        VecD<V> w;
+        w.load(k.weights + site);
         const double ln2 = 0.693147180559945309417232121458;
-        if (w.x != 0.0) lnl += w.x * (log(s0) + (double)e0 * ln2);
-        if (w.y != 0.0) lnl += w.y * (log(s1) + (double)e1 * ln2);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          double s = 0.0;
+#pragma unroll
+          for (int c = 0; c < C; ++c) s += fma(pi1, out[c][1].v[v], pi0 * out[c][0].v[v]) / k.cats;
+          if (w.v[v] != 0.0) lnl += w.v[v] * (log(s) + (double)e_in[v] * ln2);
+        }
       }
     }
   }
