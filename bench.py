@@ -94,18 +94,23 @@ class ClockSampler:
 _REF = {}
 
 
-def _ref_worker_init(taxa, patterns, chunk, worker_base):
-    """Runs in a spawned process: import the compiled, unmodified reference and prepare one chunk."""
+def _ref_worker_init(taxa, patterns, chunk, counter):
+    """Runs in a spawned process: import the compiled, unmodified reference; when `counter` is given,
+    take the next block index and prepare that chunk of the alignment."""
     import random
     sys.path.insert(0, os.path.join(REPO, "oracle", "_ref"))
     import config as rconfig      # the reference's modules (oracle/_ref/*.so)
     import mcmc_gamma as rmcmc
     import ML_gamma as rml
     from cybayes_b200.synthetic import SyntheticAlignment
-    wid = worker_base + (os.getpid() % 100000)
     aln = SyntheticAlignment(taxa, patterns, 2, SEED, block_sites=chunk)
-    _REF.update(aln=aln, rml=rml, rconfig=rconfig, rmcmc=rmcmc, chunk=chunk, wid=wid)
+    _REF.update(aln=aln, rml=rml, rconfig=rconfig, rmcmc=rmcmc, chunk=chunk)
     random.seed(1)
+    if counter is not None:
+        with counter.get_lock():
+            idx = counter.value
+            counter.value += 1
+        _ref_prepare(idx % max(1, patterns // chunk))
 
 
 def _ref_prepare(block_index):
@@ -145,10 +150,15 @@ def run_reference_arm(a):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (oracle/build_ref.sh)"}))
         return
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:  # each worker holds ~0.2 GB of leaves and produces a ~0.7 GB cache per call
+        import psutil
+        cores = max(1, min(cores, int(psutil.virtual_memory().available / 1.5e9)))
+    except Exception:
+        pass
     ctx = mp.get_context("spawn")
-    with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(a.taxa, a.patterns, a.ref_chunk, 0)) as pool:
-        pool.map(_ref_prepare, range(cores), chunksize=1)
+    counter = ctx.Value("i", 0)
+    with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(a.taxa, a.patterns, a.ref_chunk, counter)) as pool:
         for _ in range(a.warmup):
             pool.map(_ref_eval, range(cores), chunksize=1)
         t0 = time.perf_counter()
@@ -189,7 +199,7 @@ def cpu_baseline_sample(a, codes_sample):
 
 
 def _ref_sample_init(taxa, patterns, codes_sample):
-    _ref_worker_init(taxa, patterns, BLOCK, 0)
+    _ref_worker_init(taxa, patterns, BLOCK, None)
     aln, rconfig, rmcmc = _REF["aln"], _REF["rconfig"], _REF["rmcmc"]
     eye = np.eye(2)
     rconfig.N_TAXA, rconfig.N_CHARS, rconfig.N_SITES = taxa, 2, codes_sample.shape[1]
@@ -346,7 +356,7 @@ def run_ours(a):
         "data_generation_s": t_gen,
     }
 
-    if rank == 0 and not a.no_extras:
+    if rank == 0 and world == 1 and not a.no_extras:
         # dirty-path evaluations (cache_matML's job) on the same alignment: random tip -> root paths
         l_full, snap = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=True)
         parents = {c: p for (p, c) in aln.tree}

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "cb_types.cuh"
+#include "kernels_dmma.cuh"
 #include "kernels_general.cuh"
 #include "kernels_pmat.cuh"
 #include "kernels_s2.cuh"
@@ -97,6 +98,7 @@ struct cb_ctx {
   int n_taxa = 0, n_states = 0, n_cats = 0, code_bytes = 1, n_amb = 0;
   int64_t n_sites = 0, P = 0;  // real and padded pattern counts
   bool family_s2 = false;
+  bool use_dmma = false;  // general family, 9 <= S <= 64: FP64 tensor-core kernel
   int s2_vec = 1;  // sites per thread of the 2-state kernel on large alignments
   int s2_minb = 3; // its __launch_bounds__ min blocks per SM (experiment knob)
   void* d_codes = nullptr;
@@ -186,6 +188,7 @@ extern "C" int cb_create(int device, cb_ctx** out) {
   if (const char* v = getenv("CYBAYES_S2_V")) c->s2_vec = (atoi(v) == 2) ? 2 : 1;
   if (const char* v = getenv("CYBAYES_S2_MINB")) c->s2_minb = (atoi(v) == 4) ? 4 : 3;
   CU(cudaFuncSetAttribute(prune_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(prune_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   *out = c;
   return 0;
 }
@@ -300,6 +303,7 @@ extern "C" int cb_set_tips(cb_ctx* c, int n_taxa, int64_t n_sites, int n_states,
   c->n_amb = n_amb;
   c->P = (n_sites + 63) / 64 * 64;
   c->family_s2 = (n_states == 2 && (n_cats == 4 || n_cats == 1));
+  c->use_dmma = !c->family_s2 && n_states >= 9 && n_states <= 64 && !getenv("CYBAYES_NO_DMMA");
   const int64_t P = c->P;
   if (dev_alloc(c, &c->d_codes, (size_t)n_taxa * P * code_bytes)) return 1;
   // padding sites carry the all-ones code (a no-op factor) and weight 0
@@ -581,7 +585,7 @@ static LaunchConst make_const(cb_ctx* c) {
 
 constexpr int MAX_CHAIN_OPS = 4096;          // longer dirty paths fall back to the level schedule
 constexpr int64_t WALK_MIN_SITES_S2 = 32768; // below this a site tile cannot fill the GPU: use levels
-constexpr int64_t WALK_MIN_SITES_GENERAL = (int64_t)1 << 62;  // general-S walk not enabled yet
+constexpr int64_t WALK_MIN_SITES_GENERAL = 32768;
 
 static int general_rows_per_chunk(int S) {
   // rows of the two P matrices staged per pass (multiple of 4, <= 64).  Prefer a footprint
@@ -618,6 +622,9 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
       if (small) CB_LAUNCH_S2(1, 1, 64, 8); else if (V == 1) CB_LAUNCH_S2(1, 1, 256, 4); else CB_LAUNCH_S2(1, 2, 256, 4);
     }
 #undef CB_LAUNCH_S2
+  } else if (c->use_dmma) {
+    dim3 grid((unsigned)(c->P / DM_T), (unsigned)n_r, (unsigned)c->n_cats);
+    prune_dmma_kernel<<<grid, DM_THREADS, dm_smem_bytes(c->n_states), c->stream>>>(kk);
   } else {
     const int R = general_rows_per_chunk(c->n_states);
     REQUIRE(R > 0, "n_states = %d does not fit the shared-memory tiling", c->n_states);
@@ -703,7 +710,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     Schedule sched = SCHED_CHAIN;
     if (!chain) {
       const bool big = c->P >= (c->family_s2 ? WALK_MIN_SITES_S2 : WALK_MIN_SITES_GENERAL);
-      sched = (big && !(flags & CB_EVAL_FORCE_LEVELS)) ? SCHED_WALK : SCHED_LEVELS;
+      sched = ((big || (flags & CB_EVAL_FORCE_WALK)) && !(flags & CB_EVAL_FORCE_LEVELS)) ? SCHED_WALK : SCHED_LEVELS;
     }
 
     order.resize(n);

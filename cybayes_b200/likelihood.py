@@ -198,6 +198,37 @@ class PartialCache:
 
 
 STORE_ROOT = os.environ.get("CYBAYES_STORE_ROOT", "0") == "1"
+# Speculative evaluation: on alignments with at least this many patterns a *full* pass first computes
+# only lnL (no partial is written except the few the walk must read back); the cache is produced by a
+# second, storing pass only if somebody uses it -- i.e. only if the proposal is accepted.  Most full-pass
+# proposals (pi, rates, alpha, SPR) are rejected, so this trades one cheap pass for an expensive one.
+LAZY_CACHE_MIN_SITES = int(os.environ.get("CYBAYES_LAZY_CACHE_MIN_SITES", str(1 << 62)))
+
+
+class LazyPartialCache(PartialCache):
+    """Cache of a full pass whose partials are only materialised (by re-running the pass with
+    stores) when first needed.  Holds what that needs: the op list, the P slots (kept alive through
+    their owners) and pi as they were at evaluation time."""
+
+    def __init__(self, engine, site_map, node_ids, plan, pslots, pi, keepalive):
+        self.engine, self._site_map, self._nodes = engine, site_map, node_ids
+        self._plan, self._pslots, self._pi, self._keep = plan, pslots, np.array(pi, dtype=np.float64), keepalive
+        self._snap = None
+
+    @property
+    def snap(self):
+        if self._snap is None:
+            _, self._snap = self.engine.eval(None, self._plan.nodes, self._plan.children, self._pslots, self._pi,
+                                             want_snapshot=True, store_root=STORE_ROOT)
+            self._keep = None
+        return self._snap
+
+    def __del__(self):
+        if self._snap is not None:
+            try:
+                self.engine.release_snapshot(self._snap)
+            except Exception:
+                pass
 
 
 def _full(pi, root, ll_mats, edges, tmats, n_cats_tables):
@@ -206,9 +237,15 @@ def _full(pi, root, ll_mats, edges, tmats, n_cats_tables):
     if plan.nodes[-1] != root:
         raise KeyError(root)
     pslots, keep = _slot_matrix(engine, tmats, plan.edge_keys)
+    nodes = plan.nodes if STORE_ROOT else plan.nodes[:-1]
+    if engine.n_patterns >= LAZY_CACHE_MIN_SITES:
+        lnl, _ = engine.eval(None, plan.nodes, plan.children, pslots, np.asarray(pi, dtype=np.float64),
+                             want_snapshot=False)
+        alive = keep + [t._block for t in tmats if isinstance(t, PMatTable)] + \
+            [o for t in tmats if isinstance(t, PMatTable) for o in t._owners.values()]
+        return np.float64(lnl), LazyPartialCache(engine, site_map, nodes.tolist(), plan, pslots, pi, alive)
     lnl, snap = engine.eval(None, plan.nodes, plan.children, pslots, np.asarray(pi, dtype=np.float64),
                             want_snapshot=True, store_root=STORE_ROOT)
-    nodes = plan.nodes if STORE_ROOT else plan.nodes[:-1]
     return np.float64(lnl), PartialCache(engine, snap, site_map, nodes.tolist())
 
 

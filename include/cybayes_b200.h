@@ -54,7 +54,8 @@ enum {
   CB_EVAL_STORE_ROOT = 2,    /* also store the root partial (the reference caches it; the fused */
                              /* root kernel does not need it)                                   */
   CB_EVAL_NO_SYNC = 4,       /* enqueue only; the result is read later with cb_result_wait      */
-  CB_EVAL_FORCE_LEVELS = 8   /* never use the single-launch path walk, even for a chain         */
+  CB_EVAL_FORCE_LEVELS = 8,  /* never use the single-launch path walk, even for a chain         */
+  CB_EVAL_FORCE_WALK = 16    /* single-launch depth-first walk even on a small alignment (tests)  */
 };
 
 const char* cb_last_error(void);

@@ -173,6 +173,14 @@ def test_random_inputs_vs_oracle(S, n_taxa, n_sites, model, gpu_backend):
         got = eng.read_partial(snap, node)
         ref = np.stack([want_cache[k][node] for k in range(C)])
         np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0)
+    # the three schedules (levels / depth-first walk, with and without keeping the cache) agree bit for bit
+    l_walk, s_walk = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=True, force_walk=True)
+    l_walk2, _ = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=False, force_walk=True)
+    l_lev, _ = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=False, force_levels=True)
+    assert l_walk == lnl and l_walk2 == lnl and l_lev == lnl
+    for node in plan.nodes.tolist()[:-1]:
+        assert np.array_equal(eng.read_partial(s_walk, node), eng.read_partial(snap, node))
+    eng.release_snapshot(s_walk)
     # (b) device-built matrices
     block2 = eng.alloc_slots(n_e * C)
     slots2 = np.arange(block2.base, block2.base + n_e * C, dtype=np.int32)
