@@ -135,29 +135,30 @@ class Engine(SlotPool):
         return out
 
     def queue_build(self, model, pi, beta, gtr, slots, d, x=None):
-        """Queue P(d) for `slots`; consecutive jobs with the same model parameters are merged
-        into ONE launch at the next evaluation (all branches x all rate categories)."""
-        job = (model, pi, float(beta), gtr, slots, d, x)
+        """Queue P(d) for `slots` (arrays or lists); consecutive jobs with the same model parameters
+        are merged into ONE launch at the next evaluation (all branches x all rate categories)."""
+        key = (model, float(beta), None if pi is None else pi.tobytes(), id(gtr), x is None)
         pend = self._pending
-        if pend:
-            m0, pi0, b0, g0, s0, d0, x0 = pend[-1]
-            same_pi = (pi0 is pi) or (pi0 is not None and pi is not None and np.array_equal(pi0, pi))
-            if m0 == model and b0 == float(beta) and g0 is gtr and same_pi and ((x0 is None) == (x is None)):
-                pend[-1] = (model, pi0, b0, g0, np.concatenate((s0, slots)), np.concatenate((d0, d)),
-                            None if x is None else np.concatenate((x0, x)))
-                return
-        pend.append(job)
+        if pend and pend[-1][0] == key:
+            job = pend[-1]
+            job[5].append(slots)
+            job[6].append(d)
+            if x is not None:
+                job[7].append(x)
+        else:
+            pend.append([key, model, pi, float(beta), gtr, [slots], [d], [] if x is None else [x]])
 
     def flush_builds(self):
         pend = self._pending
         if not pend:
             return
         self._pending = []
-        for model, pi, beta, gtr, slots, d, x in pend:
-            slots = np.ascontiguousarray(slots, dtype=np.int32)
-            d = np.ascontiguousarray(d, dtype=np.float64)
+        cat = np.concatenate
+        for _, model, pi, beta, gtr, slots, d, x in pend:
+            slots = np.ascontiguousarray(cat(slots) if len(slots) > 1 else slots[0], dtype=np.int32)
+            d = np.ascontiguousarray(cat(d) if len(d) > 1 else d[0], dtype=np.float64)
+            x_a = None if not x else np.ascontiguousarray(cat(x) if len(x) > 1 else x[0], dtype=np.float64)
             pi_a = None if pi is None else np.ascontiguousarray(pi, dtype=np.float64)
-            x_a = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
             check(self._lib.cb_pmat_build(self._ctx, int(model), None if pi_a is None else _f64(pi_a), beta,
                                           None if gtr is None else _f64(gtr), slots.size, _i32(slots), _f64(d),
                                           None if x_a is None else _f64(x_a)))

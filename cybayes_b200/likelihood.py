@@ -97,28 +97,44 @@ def reset_engines():
 class _Plan:
     """Edge list -> node operations.  `nodes[i]` is completed by the i-th op in the order in
     which the reference finishes parents while walking `edges` (ML_gamma.pyx:24-36)."""
-    __slots__ = ("edges", "nodes", "children", "edge_keys", "kids", "index")
+    __slots__ = ("edges", "node_list", "kids", "index", "_nodes", "_children", "_edge_keys")
 
     def __init__(self, edges):
         self.edges = list(edges)
-        first = {}
-        nodes, children, kids = [], [], {}
+        first, kids, node_list = {}, {}, []
+        get = first.get
         for parent, child in self.edges:
-            if parent in first:
-                c0 = first.pop(parent)
-                kids[parent] = (c0, child)
-                nodes.append(parent)
-                children.append(c0)
-                children.append(child)
-            else:
+            c0 = get(parent)
+            if c0 is None:
                 first[parent] = child
-        if first:
-            raise ValueError(f"nodes with a single child edge: {sorted(first)}")
-        self.kids = kids
-        self.index = {n: i for i, n in enumerate(nodes)}
-        self.nodes = np.array(nodes, dtype=np.int32)
-        self.children = np.array(children, dtype=np.int32)
-        self.edge_keys = [(n, c) for n in nodes for c in kids[n]]
+            else:
+                kids[parent] = (c0, child)
+                node_list.append(parent)
+        if 2 * len(kids) != len(self.edges):
+            raise ValueError("every internal node needs exactly two child edges")
+        self.kids, self.node_list = kids, node_list
+        self.index = dict(zip(node_list, range(len(node_list))))
+        self._nodes = self._children = self._edge_keys = None
+
+    @property
+    def nodes(self):
+        if self._nodes is None:
+            self._nodes = np.array(self.node_list, dtype=np.int32)
+        return self._nodes
+
+    @property
+    def children(self):
+        if self._children is None:
+            kids = self.kids
+            self._children = np.array([c for n in self.node_list for c in kids[n]], dtype=np.int32)
+        return self._children
+
+    @property
+    def edge_keys(self):
+        if self._edge_keys is None:
+            kids = self.kids
+            self._edge_keys = [(n, c) for n in self.node_list for c in kids[n]]
+        return self._edge_keys
 
 
 _plan_cache = []  # small MRU list of plans, matched by list equality

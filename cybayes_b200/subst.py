@@ -129,7 +129,7 @@ def table_from_host(engine, mapping):
     """Upload a reference-style ``{edge: ndarray}`` dict (host buffers) into a PMatTable."""
     edges = list(mapping.keys())
     block = engine.alloc_slots(len(edges))
-    mats = np.stack([np.asarray(mapping[e], dtype=np.float64) for e in edges])
+    mats = np.array(list(mapping.values()), dtype=np.float64)
     engine.upload_pmats(np.arange(block.base, block.base + block.n, dtype=np.int32), mats)
     return PMatTable(engine, edges, block)
 
@@ -189,7 +189,7 @@ def _queue(engine, model_name, binary, pi, rates, slots, d, norm_beta):
     if 0 < n <= HOST_EXP_MAX:
         exp = math.exp
         nb = -beta
-        x = np.array([exp(nb * v) for v in d.tolist()])
+        x = [exp(nb * v) for v in (d.tolist() if isinstance(d, np.ndarray) else d)]
     if model_name == "JC":
         engine.queue_build(CB_MODEL_JC, pi_a, beta, None, slots, d, x)
     elif model_name == "F81":
@@ -221,8 +221,7 @@ def get_edge_transition_mat(pi, rates, d, n_cats=None):
     if model == "F81":
         config.NORM_BETA = f81_beta(np.asarray(pi))
     block = engine.alloc_slots(1)
-    _queue(engine, model, config.IN_DTYPE == "bin", pi, rates, np.array([block.base], dtype=np.int32),
-           np.array([d], dtype=np.float64), config.NORM_BETA)
+    _queue(engine, model, config.IN_DTYPE == "bin", pi, rates, [block.base], [float(d)], config.NORM_BETA)
     return PMatrix(engine, block.base, block)
 
 

@@ -62,3 +62,36 @@ def gpu_backend():
     likelihood._plan_cache.clear()
     yield likelihood
     likelihood.reset_engines()
+
+
+def run_reference_script(script_name, argv, monkeypatch, capsys):
+    """Run one of the reference's unmodified, byte-compiled driver scripts (oracle/_ref/<name>.code, or
+    the .py under /root/reference when that exists) on top of cybayes_b200/compat; returns its stdout."""
+    import runpy
+    path = os.path.join(REPO, "oracle", "_ref", script_name + ".code")
+    if not os.path.exists(path):
+        path = os.path.join("/root/reference", script_name + ".py")
+    if not os.path.exists(path):
+        pytest.skip("no reference driver available (oracle/build_ref.sh)")
+    monkeypatch.syspath_prepend(os.path.join(REPO, "cybayes_b200", "compat"))
+    names = ("config", "utils", "mcmc_gamma", "ML_gamma", "mcmc", "ML")
+    for m in names:
+        monkeypatch.delitem(sys.modules, m, raising=False)
+    monkeypatch.setattr(sys, "argv", [script_name + ".py"] + list(argv))
+    try:
+        runpy.run_path(path, run_name="__main__")
+    finally:
+        for m in names:
+            sys.modules.pop(m, None)
+    return capsys.readouterr().out
+
+
+def check_nongamma_trace(out, name, rel):
+    rows, meta = load_trace(name)
+    gens = [l.split("\t") for l in out.splitlines() if len(l.split("\t")) == 6 and l.split("\t")[0].isdigit()]
+    assert len(gens) == len(rows)
+    for f, g in zip(gens, rows):
+        assert (f[4], f[5], f[3]) == (g["param"], g["move"], g["TL"]), (f, g)
+        for col, idx in (("state_lnL", 1), ("proposed_ll", 2)):
+            want = float(g[col])
+            assert abs(float(f[idx]) - want) <= rel * abs(want), (f, g)

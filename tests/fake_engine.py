@@ -54,7 +54,7 @@ class FakeEngine(SlotPool):
             S = self.n_states
             lam, U, Uinv = gtr[:S], gtr[S:S + S * S].reshape(S, S), gtr[S + S * S:].reshape(S, S)
             Q = (U * lam) @ Uinv  # the rate matrix back from its eigensystem
-        for s, dd in zip(np.asarray(slots).tolist(), np.asarray(d).tolist()):
+        for s, dd in zip(np.asarray(slots).tolist(), np.asarray(d, dtype=float).tolist()):
             if name == "GTR":
                 self.pm[s] = oracle._linalg.expm(Q * dd) if self.gtr_via == "expm" else (U * np.exp(lam * dd)) @ Uinv
             else:

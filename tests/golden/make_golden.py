@@ -198,5 +198,31 @@ def main():
         json.dump({"generator": "tests/golden/make_golden.py", "cases": cases}, fh, indent=0)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "--nongamma"):
     main()
+
+
+# ---- non-Gamma driver (mat_mcmc.py + mcmc.pyx + ML.pyx): traces only -------------------------------
+NONGAMMA = [("ng_binary_F81", "binary.phy", "F81", "bin", 300), ("ng_phon_ringe_JC", "phon_ringe.phy", "JC", "multi", 300),
+            ("ng_narrow_F81", "narrow.phy", "F81", "bin", 400)]
+
+
+def run_trace_nongamma(name, fname, model, dtype, n_gen):
+    out_prefix = f"/tmp/golden_{name}"
+    cmd = [sys.executable, "mat_mcmc.code", "-i", os.path.join(REF_DATA, fname), "-m", model, "-n", str(n_gen),
+           "-t", "1", "-d", dtype, "-o", out_prefix]
+    res = subprocess.run(cmd, cwd=REF_BUILD, capture_output=True, text=True, check=True)
+    gens = [l.split("\t") for l in res.stdout.splitlines() if len(l.split("\t")) == 6 and l.split("\t")[0].isdigit()]
+    init = [l for l in res.stdout.splitlines() if l.startswith("Initial Likelihood")][0].split()[-1]
+    assert len(gens) == n_gen
+    with open(os.path.join(HERE, "traces", name + ".tsv"), "w") as fh:
+        fh.write(f"# unmodified reference driver mat_mcmc.py, seed 1234, -n {n_gen} -t 1; init_lnL={init}\n")
+        fh.write("iter\tstate_lnL\tproposed_ll\tTL\tparam\tmove\n")
+        for g in gens:
+            fh.write("\t".join(g) + "\n")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--nongamma":
+    for args in NONGAMMA:
+        run_trace_nongamma(*args)
+        print("trace", args[0])

@@ -379,3 +379,16 @@ def test_unmodified_reference_driver_runs_on_the_engine(golden_cases, gpu_backen
         assert f[3] == g["TL"], (f, g)
     for m in ("config", "utils", "mcmc_gamma", "ML_gamma", "mcmc", "ML"):
         sys.modules.pop(m, None)
+
+
+@pytest.mark.parametrize("name,fname,model,dtype,n_gen", [("ng_binary_F81", "binary.phy", "F81", "bin", 300),
+                                                          ("ng_phon_ringe_JC", "phon_ringe.phy", "JC", "multi", 300),
+                                                          ("ng_narrow_F81", "narrow.phy", "F81", "bin", 400)])
+def test_unmodified_non_gamma_driver_runs_on_the_engine(name, fname, model, dtype, n_gen, gpu_backend, tmp_path,
+                                                        monkeypatch, capsys):
+    """The reference's single-rate driver mat_mcmc.py, unmodified, on the CUDA engine (n_cats = 1)."""
+    from conftest import check_nongamma_trace, run_reference_script
+    out = run_reference_script("mat_mcmc", ["-i", os.path.join(REPO, "tests", "golden", "data", fname), "-m", model,
+                                            "-n", str(n_gen), "-t", "1", "-d", dtype, "-o", str(tmp_path / "ng")],
+                               monkeypatch, capsys)
+    check_nongamma_trace(out, name, REL_CLOSED)

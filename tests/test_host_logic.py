@@ -247,3 +247,16 @@ def test_non_gamma_surface(golden_cases, fake_backend):
     tm2 = [oracle.prob_t("F81", False, np.asarray(st["pi"]), tree2, None, 1.0)]
     want2 = oracle.mat_ml(np.asarray(st["pi"]), st["root"], ll, st["postorder"], tm2 * 1, n_sites, config.N_TAXA, 1)[0]
     assert abs(l2 - want2) <= 1e-12 * abs(want2)
+
+
+@pytest.mark.parametrize("name,fname,model,dtype,n_gen", [("ng_binary_F81", "binary.phy", "F81", "bin", 300),
+                                                          ("ng_phon_ringe_JC", "phon_ringe.phy", "JC", "multi", 300)])
+def test_unmodified_non_gamma_driver_on_compat_modules(name, fname, model, dtype, n_gen, fake_backend, tmp_path,
+                                                       monkeypatch, capsys):
+    """mat_mcmc.py (single-rate surface: mcmc + ML) unchanged, including its quirk of not refreshing
+    the cache after accepted branch moves (mat_mcmc.py:141-152)."""
+    from conftest import check_nongamma_trace, run_reference_script
+    out = run_reference_script("mat_mcmc", ["-i", os.path.join(REPO, "tests", "golden", "data", fname), "-m", model,
+                                            "-n", str(n_gen), "-t", "1", "-d", dtype, "-o", str(tmp_path / "ng")],
+                               monkeypatch, capsys)
+    check_nongamma_trace(out, name, 1e-10)
