@@ -384,6 +384,14 @@ def run_ours(a):
                                  "kernel_ms": statistics.mean(ms[2:]), "launches_per_eval": 1,
                                  "check": "each equals the full-pass lnL bit for bit"}
         eng.release_snapshot(snap)
+        # likelihood only (no cache kept): what a proposal that is going to be rejected costs
+        ms = []
+        for _ in range(6):
+            l_only, _ = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=False)
+            ms.append(eng.last_eval_ms())
+        assert l_only == l_full
+        out["lnl_only"] = {"evals_per_sec": 1e3 / statistics.mean(ms[2:]), "kernel_ms": statistics.mean(ms[2:]),
+                           "note": "same walk, only the partials that must be read back are written"}
 
     if rank == 0 and world == 1 and not a.no_extras:
         # CPU baseline beside it: the compiled reference, 1 core, on a bounded sample of the same data,

@@ -98,7 +98,7 @@ struct cb_ctx {
   int n_taxa = 0, n_states = 0, n_cats = 0, code_bytes = 1, n_amb = 0;
   int64_t n_sites = 0, P = 0;  // real and padded pattern counts
   bool family_s2 = false;
-  bool use_dmma = false;  // general family, 9 <= S <= 64: FP64 tensor-core kernel
+  bool use_dmma = false;  // general family, 32 <= S <= 64: FP64 tensor-core kernel (below that the plain kernel wins)
   int s2_vec = 1;  // sites per thread of the 2-state kernel on large alignments
   int s2_minb = 3; // its __launch_bounds__ min blocks per SM (experiment knob)
   void* d_codes = nullptr;
@@ -303,7 +303,7 @@ extern "C" int cb_set_tips(cb_ctx* c, int n_taxa, int64_t n_sites, int n_states,
   c->n_amb = n_amb;
   c->P = (n_sites + 63) / 64 * 64;
   c->family_s2 = (n_states == 2 && (n_cats == 4 || n_cats == 1));
-  c->use_dmma = !c->family_s2 && n_states >= 9 && n_states <= 64 && !getenv("CYBAYES_NO_DMMA");
+  c->use_dmma = !c->family_s2 && n_states >= 32 && n_states <= 64 && !getenv("CYBAYES_NO_DMMA");
   const int64_t P = c->P;
   if (dev_alloc(c, &c->d_codes, (size_t)n_taxa * P * code_bytes)) return 1;
   // padding sites carry the all-ones code (a no-op factor) and weight 0
@@ -663,7 +663,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   const bool store_root = (flags & CB_EVAL_STORE_ROOT) != 0;
   REQUIRE(!(want_snap && n_lists != 1), "snapshots are only kept for single evaluations");
   CU(cudaSetDevice(c->device));
-  if (ensure_staging(c, total_ops, total_ops, n_lists)) return 1;
+  if (ensure_staging(c, total_ops, total_ops + n_lists, n_lists)) return 1;
   CU(cudaEventSynchronize(c->ev_stage));  // previous H2D of the staging area finished
 
   const Snapshot* sin = snapshot_in >= 0 ? &c->snaps[snapshot_in] : nullptr;
@@ -675,7 +675,8 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   std::vector<int> launch_maxops;
   bool single_launch = true;
   std::vector<int>& order = c->order;    // position -> original op index (per list)
-  std::vector<int> pos_of, n_sub, kid_op[2];
+  std::vector<int> pos_of, n_sub, kid_op[2], range_id;
+  std::vector<std::pair<int, int>> walk_segs;
   std::vector<char> read_back;
 
   for (int li = 0; li < n_lists; ++li) {
@@ -721,26 +722,78 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
       for (int i = 0; i < n; ++i)
         for (int kx = 0; kx < 2; ++kx)
           if (kid_op[kx][i] >= 0) n_sub[i] += n_sub[kid_op[kx][i]];
-      // iterative post-order from the root op, heavier child subtree first
-      std::vector<int> stack, out;
-      std::vector<char> expanded(n, 0);
-      out.reserve(n);
-      stack.push_back(n - 1);
-      while (!stack.empty()) {
-        const int i = stack.back();
-        if (expanded[i]) {
-          stack.pop_back();
-          out.push_back(i);
-          continue;
-        }
-        expanded[i] = 1;
-        int a0 = kid_op[0][i], a1 = kid_op[1][i];
-        if (a0 >= 0 && a1 >= 0 && n_sub[a1] > n_sub[a0]) std::swap(a0, a1);  // a0 = heavier
-        if (a1 >= 0) stack.push_back(a1);  // lighter: visited second (pushed first)
-        if (a0 >= 0) stack.push_back(a0);
+      // Post-order from the root op, heavier child subtree first.  When the alignment gives too few
+      // site tiles to fill the GPU for a whole sequential walk (small shards), the tree is cut into
+      // independent subtrees of at most `limit` ops that run as parallel ranges of a first launch;
+      // the ops above the cut follow in a second launch.
+      int limit = n + 1;
+      {
+        const int64_t tile_sites = c->family_s2 ? (int64_t)256 * c->s2_vec : (c->use_dmma ? DM_T : GEN_T);
+        const int64_t blocks = (c->P + tile_sites - 1) / tile_sites * (c->family_s2 ? 1 : c->n_cats);
+        const int64_t slots = (int64_t)c->sm_count * (c->family_s2 ? (c->s2_vec == 1 ? 3 : 2) : 2);
+        if (blocks < 4 * slots && n >= 64 && !(flags & CB_EVAL_FORCE_WALK))
+          limit = std::max(16, std::min(256, (int)(n * blocks / (8 * slots)) + 1));
+        if (getenv("CYBAYES_WALK_SPLIT")) limit = std::max(2, atoi(getenv("CYBAYES_WALK_SPLIT")));
+        if (limit >= n) limit = n + 1;  // nothing to cut
       }
-      if ((int)out.size() == n) order = out; else sched = SCHED_LEVELS;  // ops not under the root
+      std::vector<int> out, top, stack;
+      std::vector<char> expanded(n, 0);
+      std::vector<std::pair<int, int>> segs;
+      out.reserve(n);
+      auto post_order = [&](int root_op) {
+        stack.clear();
+        stack.push_back(root_op);
+        while (!stack.empty()) {
+          const int i = stack.back();
+          if (expanded[i]) {
+            stack.pop_back();
+            out.push_back(i);
+            continue;
+          }
+          expanded[i] = 1;
+          int a0 = kid_op[0][i], a1 = kid_op[1][i];
+          if (a0 >= 0 && a1 >= 0 && n_sub[a1] > n_sub[a0]) std::swap(a0, a1);  // a0 = heavier
+          if (a1 >= 0) stack.push_back(a1);  // lighter: visited second (pushed first)
+          if (a0 >= 0) stack.push_back(a0);
+        }
+      };
+      if (limit > n) {
+        post_order(n - 1);
+      } else {
+        // walk down from the root: ops with a subtree above the limit stay in `top`
+        std::vector<std::pair<int, int>> st2;  // (op, phase)
+        std::vector<int> cut;
+        st2.push_back({n - 1, 0});
+        while (!st2.empty()) {
+          auto [i, phase] = st2.back();
+          st2.pop_back();
+          if (phase == 1) { top.push_back(i); continue; }
+          if (n_sub[i] <= limit) { cut.push_back(i); continue; }
+          st2.push_back({i, 1});
+          int a0 = kid_op[0][i], a1 = kid_op[1][i];
+          if (a0 >= 0 && a1 >= 0 && n_sub[a1] > n_sub[a0]) std::swap(a0, a1);
+          if (a1 >= 0) st2.push_back({a1, 0});
+          if (a0 >= 0) st2.push_back({a0, 0});
+        }
+        std::stable_sort(cut.begin(), cut.end(), [&](int x, int y) { return n_sub[x] > n_sub[y]; });  // big first
+        for (int r : cut) {
+          const int b0 = (int)out.size();
+          post_order(r);
+          segs.push_back({b0, (int)out.size()});
+        }
+        for (int i : top) out.push_back(i);
+      }
+      if ((int)out.size() == n) {
+        order = out;
+        range_id.assign(n, 0);
+        for (size_t si = 0; si < segs.size(); ++si)
+          for (int p = segs[si].first; p < segs[si].second; ++p) range_id[p] = (int)si + 1;
+        walk_segs = segs;
+      } else {
+        sched = SCHED_LEVELS;  // ops not under the root
+      }
     }
+    if (sched != SCHED_WALK) { range_id.assign(n, 0); walk_segs.clear(); }
     pos_of.assign(n, 0);
     for (int p = 0; p < n; ++p) pos_of[order[p]] = p;
     // which ops are read back from memory by a later op (as opposed to carried on chip)?
@@ -748,7 +801,8 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     for (int i = 0; i < n; ++i)
       for (int kx = 0; kx < 2; ++kx) {
         const int k0 = kid_op[kx][i];
-        if (k0 >= 0 && !(sched != SCHED_LEVELS && pos_of[k0] == pos_of[i] - 1)) read_back[k0] = 1;
+        if (k0 >= 0 && !(sched != SCHED_LEVELS && pos_of[k0] == pos_of[i] - 1 && range_id[pos_of[k0]] == range_id[pos_of[i]]))
+          read_back[k0] = 1;
       }
 
     for (int p = 0; p < n; ++p) {
@@ -782,7 +836,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
           op.src[kx] = (const char*)c->d_codes + (size_t)(ch - 1) * c->P * c->code_bytes;
         } else if (kid_op[kx][i0] >= 0) {
           const int pp = pos_of[kid_op[kx][i0]];
-          if (sched != SCHED_LEVELS && pp == p - 1) {
+          if (sched != SCHED_LEVELS && pp == p - 1 && range_id[pp] == range_id[p]) {
             op.kind[kx] = SRC_CARRIED;
           } else {
             const OpDesc& prod = c->h_ops[b + pp];
@@ -808,7 +862,22 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
       }
     }
 
-    if (sched != SCHED_LEVELS) {
+    if (sched == SCHED_WALK && !walk_segs.empty()) {
+      single_launch = false;
+      const int start = n_ranges;
+      int mx = 1;
+      for (auto& sg : walk_segs) {
+        RangeDesc& r = c->h_ranges[n_ranges++];
+        r.begin = b + sg.first; r.end = b + sg.second; r.out_index = -1; r.pad_ = 0;
+        mx = std::max(mx, sg.second - sg.first);
+      }
+      launches.push_back({start, n_ranges});
+      launch_maxops.push_back(mx);
+      RangeDesc& r = c->h_ranges[n_ranges++];
+      r.begin = b + walk_segs.back().second; r.end = e; r.out_index = li; r.pad_ = 0;
+      launches.push_back({n_ranges - 1, n_ranges});
+      launch_maxops.push_back(r.end - r.begin);
+    } else if (sched != SCHED_LEVELS) {
       RangeDesc& r = c->h_ranges[n_ranges++];
       r.begin = b; r.end = e; r.out_index = li; r.pad_ = 0;
     } else {

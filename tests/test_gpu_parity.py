@@ -178,6 +178,17 @@ def test_random_inputs_vs_oracle(S, n_taxa, n_sites, model, gpu_backend):
     l_walk2, _ = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=False, force_walk=True)
     l_lev, _ = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=False, force_levels=True)
     assert l_walk == lnl and l_walk2 == lnl and l_lev == lnl
+    # small shards cut the walk into parallel subtrees + a top part (two launches): same bits
+    os.environ["CYBAYES_WALK_SPLIT"] = "3"
+    try:
+        l_split, s_split = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=True, force_walk=True)
+        l_split2, _ = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=False, force_walk=True)
+    finally:
+        del os.environ["CYBAYES_WALK_SPLIT"]
+    assert l_split == lnl and l_split2 == lnl
+    for node in plan.nodes.tolist()[:-1]:
+        assert np.array_equal(eng.read_partial(s_split, node), eng.read_partial(snap, node))
+    eng.release_snapshot(s_split)
     for node in plan.nodes.tolist()[:-1]:
         assert np.array_equal(eng.read_partial(s_walk, node), eng.read_partial(snap, node))
     eng.release_snapshot(s_walk)
