@@ -188,7 +188,9 @@ extern "C" int cb_create(int device, cb_ctx** out) {
   if (const char* v = getenv("CYBAYES_S2_V")) c->s2_vec = (atoi(v) == 2) ? 2 : 1;
   if (const char* v = getenv("CYBAYES_S2_MINB")) c->s2_minb = (atoi(v) == 4) ? 4 : 3;
   CU(cudaFuncSetAttribute(prune_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(prune_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define CB_DMMA_ATTR(SS) CU(cudaFuncSetAttribute(prune_dmma_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+  CB_DMMA_ATTR(0); CB_DMMA_ATTR(32); CB_DMMA_ATTR(40); CB_DMMA_ATTR(47); CB_DMMA_ATTR(48); CB_DMMA_ATTR(56); CB_DMMA_ATTR(64);
+#undef CB_DMMA_ATTR
   *out = c;
   return 0;
 }
@@ -624,7 +626,13 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
 #undef CB_LAUNCH_S2
   } else if (c->use_dmma) {
     dim3 grid((unsigned)(c->P / DM_T), (unsigned)n_r, (unsigned)c->n_cats);
-    prune_dmma_kernel<<<grid, DM_THREADS, dm_smem_bytes(c->n_states), c->stream>>>(kk);
+    const size_t smem = dm_smem_bytes(c->n_states);
+    switch (c->n_states) {  // compile-time state counts for the common sizes, run-time S otherwise
+#define CB_DMMA_CASE(SS) case SS: prune_dmma_kernel<SS><<<grid, DM_THREADS, smem, c->stream>>>(kk); break
+      CB_DMMA_CASE(32); CB_DMMA_CASE(40); CB_DMMA_CASE(47); CB_DMMA_CASE(48); CB_DMMA_CASE(56); CB_DMMA_CASE(64);
+#undef CB_DMMA_CASE
+      default: prune_dmma_kernel<0><<<grid, DM_THREADS, smem, c->stream>>>(kk);
+    }
   } else {
     const int R = general_rows_per_chunk(c->n_states);
     REQUIRE(R > 0, "n_states = %d does not fit the shared-memory tiling", c->n_states);

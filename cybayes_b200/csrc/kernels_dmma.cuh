@@ -33,7 +33,7 @@ __host__ __device__ inline int dm_ps(int S) {  // P row stride: >= S rounded to 
 }
 __host__ __device__ inline size_t dm_smem_bytes(int S) {
   const int S8 = dm_s8(S);
-  return sizeof(double) * ((size_t)S8 * dm_ps(S) + (size_t)S8 * DM_LS + S8 + 4 * DM_T) + sizeof(int) * (size_t)(2 * DM_T);
+  return sizeof(double) * ((size_t)2 * S8 * dm_ps(S) + (size_t)S8 * DM_LS + S8 + 4 * DM_T) + sizeof(int) * (size_t)(2 * DM_T);
 }
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
@@ -41,17 +41,43 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Shared memory holds ONE P matrix and ONE [S8][72] tile: the two children of a node are contracted
-// one after the other into register accumulators (the carried child first, since it is already in
-// the tile), and the product is written back into the same tile, which then is the carried partial
-// of the next op.  ~72 KB at S = 64, so two to three blocks share an SM and one block's staging
-// overlaps another's tensor work.
+// global (row-major S x S) -> shared (row stride PS) without touching registers
+__device__ __forceinline__ void stage_p_async(double* Pm, const double* pm, int S, int PS, int warp, int lane) {
+  if ((S & 1) == 0) {
+    const int h = S >> 1;
+    for (int i = warp; i < S; i += DM_THREADS / 32)
+      for (int jj = lane; jj < h; jj += 32) cp_async16(Pm + i * PS + 2 * jj, pm + i * S + 2 * jj);
+  } else {
+    for (int i = warp; i < S; i += DM_THREADS / 32)
+      for (int j = lane; j < S; j += 32) cp_async8(Pm + i * PS + j, pm + i * S + j);
+  }
+}
+
+// Shared memory holds the P matrices of both children (the second one streams in with cp.async while
+// the tensor cores work on the first) and ONE [S8][72] tile: the two children are contracted one after
+// the other into register accumulators (the carried child first, since it already is in the tile),
+// and the product is written back into the same tile, which then is the carried partial of the next
+// op.  ~107 KB at S = 64: two blocks share an SM, so one block's staging overlaps the other's tensor work.
+// SCT = compile-time state count (0 = take it from the launch constants): with S known the staging,
+// contraction and finalise loops unroll and their index arithmetic folds into immediates.
+template <int SCT>
 __global__ void __launch_bounds__(DM_THREADS, 2) prune_dmma_kernel(const LaunchConst k) {
   extern __shared__ __align__(16) double dsm[];
-  const int S = k.n_states, S8 = dm_s8(S), S4 = (S + 3) / 4 * 4, PS = dm_ps(S);
-  double* Pm = dsm;                              // [S8][PS]
-  double* tile = Pm + S8 * PS;                   // [S8][DM_LS]
+  const int S = SCT ? SCT : k.n_states;
+  const int S8 = dm_s8(S), S4 = (S + 3) / 4 * 4, PS = dm_ps(S);
+  double* Pm0 = dsm;                             // [2][S8][PS]
+  double* tile = Pm0 + 2 * S8 * PS;              // [S8][DM_LS]
   double* rowsum = tile + S8 * DM_LS;            // [S8]
   double* colmax = rowsum + S8;                  // [4][DM_T]
   int* codes = reinterpret_cast<int*>(colmax + 4 * DM_T);  // [DM_T]
@@ -69,7 +95,8 @@ __global__ void __launch_bounds__(DM_THREADS, 2) prune_dmma_kernel(const LaunchC
   const int fs = tid & (DM_T - 1), fg = tid >> 6;  // finalise mapping: site, row group (4 groups)
 
   // zero once: padded rows / columns must stay 0 (never NaN) for the whole kernel
-  for (int i = tid; i < S8 * PS + S8 * DM_LS + S8 + 4 * DM_T; i += DM_THREADS) dsm[i] = 0.0;
+  for (int i = tid; i < 2 * S8 * PS + S8 * DM_LS + S8 + 4 * DM_T; i += DM_THREADS) dsm[i] = 0.0;
+  __syncthreads();
 
 #pragma unroll 1
   for (int o = rg.begin; o < rg.end; ++o) {
@@ -77,30 +104,29 @@ __global__ void __launch_bounds__(DM_THREADS, 2) prune_dmma_kernel(const LaunchC
     const int first = (op->kind[1] == SRC_CARRIED) ? 1 : 0;  // the carried child already sits in the tile
     double prod[DM_MAX_MT][2][2];
     int e_sum = 0;
+    // both P matrices start streaming now: group 0 = first child (+ its tile), group 1 = second child's P
+    stage_p_async(Pm0, k.pmats + (int64_t)op->pslot[first][c] * S * S, S, PS, warp, lane);
+    {
+      const int kind = op->kind[first];
+      if (kind == SRC_BUFFER) {
+        const double* src = static_cast<const double*>(op->src[first]) + (int64_t)c * S * P + site0;
+        for (int j = warp; j < S; j += 8) cp_async16(tile + j * DM_LS + lane * 2, src + (int64_t)j * P + lane * 2);
+      }
+    }
+    cp_async_commit();
+    stage_p_async(Pm0 + S8 * PS, k.pmats + (int64_t)op->pslot[1 - first][c] * S * S, S, PS, warp, lane);
+    cp_async_commit();
 #pragma unroll 1
     for (int step = 0; step < 2; ++step) {
       const int ch = step ? 1 - first : first;
       const int kind = op->kind[ch];
-      __syncthreads();  // P, codes and (unless carried) the tile are free
-      {
-        const double* pm = k.pmats + (int64_t)op->pslot[ch][c] * S * S;
-        if ((S & 1) == 0) {
-          const int h = S >> 1;
-          for (int idx = tid; idx < S * h; idx += DM_THREADS) {
-            const int i = idx / h, j = (idx - i * h) * 2;
-            *reinterpret_cast<double2*>(Pm + i * PS + j) = __ldg(reinterpret_cast<const double2*>(pm + i * S + j));
-          }
-        } else {
-          for (int idx = tid; idx < S * S; idx += DM_THREADS) {
-            const int i = idx / S, j = idx - i * S;
-            Pm[i * PS + j] = __ldg(pm + idx);
-          }
-        }
+      const double* Pm = Pm0 + step * S8 * PS;
+      if (step == 1 && kind == SRC_BUFFER) {  // the tile is free now (barrier at the end of step 0)
+        const double* src = static_cast<const double*>(op->src[ch]) + (int64_t)c * S * P + site0;
+        for (int j = warp; j < S; j += 8) cp_async16(tile + j * DM_LS + lane * 2, src + (int64_t)j * P + lane * 2);
+        cp_async_commit();
       }
       if (kind == SRC_BUFFER) {
-        const double* src = static_cast<const double*>(op->src[ch]) + (int64_t)c * S * P + site0;
-        for (int j = warp; j < S; j += 8)
-          *reinterpret_cast<double2*>(tile + j * DM_LS + lane * 2) = ld_cg2(src + (int64_t)j * P + lane * 2);
         e_sum += __ldcg(op->src_scale[ch] + (int64_t)c * P + site0 + fs);
       } else if (kind == SRC_TIP) {
         if (tid < DM_T)
@@ -109,6 +135,7 @@ __global__ void __launch_bounds__(DM_THREADS, 2) prune_dmma_kernel(const LaunchC
       } else {
         e_sum += cur_e[fs];
       }
+      if (step == 0) cp_async_wait<1>(); else cp_async_wait<0>();
       __syncthreads();
       double acc[DM_MAX_MT][2][2];
 #pragma unroll
@@ -116,27 +143,40 @@ __global__ void __launch_bounds__(DM_THREADS, 2) prune_dmma_kernel(const LaunchC
 #pragma unroll
         for (int n = 0; n < 2; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
       if (kind != SRC_TIP) {
+        const double* bp = tile + t4 * DM_LS + n0 + g;
+        const double* ap = Pm + (wm * 8 + g) * PS + t4;
+        const int a_step = 16 * PS;  // two m-tiles down (the other warp row owns the one in between)
+#pragma unroll 2
         for (int k0 = 0; k0 < S4; k0 += 4) {
-          const double b0 = tile[(k0 + t4) * DM_LS + n0 + g];
-          const double b1 = tile[(k0 + t4) * DM_LS + n0 + 8 + g];
+          const double b0 = bp[0], b1 = bp[8];
 #pragma unroll
           for (int m = 0; m < DM_MAX_MT; ++m) {
-            const int mt = wm + 2 * m;
-            if (mt < n_mt) {
-              const double a = Pm[(mt * 8 + g) * PS + k0 + t4];
+            if (wm + 2 * m < n_mt) {
+              const double a = ap[m * a_step];
               dmma_8x8x4(acc[m][0][0], acc[m][0][1], a, b0);
               dmma_8x8x4(acc[m][1][0], acc[m][1][1], a, b1);
             }
           }
+          bp += 4 * DM_LS;
+          ap += 4;
         }
       } else {
-        for (int i = tid; i < S; i += DM_THREADS) {
-          const double* row = Pm + i * PS;
+        // row sums are only needed for '?' / '-' cells (code == S): skip them when the tile has none;
+        // otherwise 4 threads per row add every fourth entry each and combine in a fixed order
+        const int any_missing = __syncthreads_or(tid < DM_T && codes[tid] == S);
+        if (any_missing) {
+          const int i = tid >> 2, q = tid & 3;
           double s = 0.0;
-          for (int j = 0; j < S; ++j) s += row[j];
-          rowsum[i] = s;
+          if (i < S) {
+            const double* row = Pm + i * PS;
+            for (int j = q; j < S; j += 4) s += row[j];
+          }
+          const double s1 = __shfl_down_sync(0xffffffffu, s, 1);
+          const double s2 = __shfl_down_sync(0xffffffffu, s, 2);
+          const double s3 = __shfl_down_sync(0xffffffffu, s, 3);
+          if (q == 0 && i < S) rowsum[i] = ((s + s1) + s2) + s3;
+          __syncthreads();
         }
-        __syncthreads();
 #pragma unroll
         for (int m = 0; m < DM_MAX_MT; ++m) {
           const int mt = wm + 2 * m;
@@ -170,8 +210,8 @@ __global__ void __launch_bounds__(DM_THREADS, 2) prune_dmma_kernel(const LaunchC
           for (int e = 0; e < 2; ++e) {
             if (step == 0) prod[m][n][e] = acc[m][n][e]; else prod[m][n][e] *= acc[m][n][e];
           }
+      __syncthreads();  // every warp is done with the tile / codes of this child
     }
-    __syncthreads();  // every warp is done reading the tile
 #pragma unroll
     for (int m = 0; m < DM_MAX_MT; ++m) {
       const int mt = wm + 2 * m;
@@ -216,6 +256,7 @@ __global__ void __launch_bounds__(DM_THREADS, 2) prune_dmma_kernel(const LaunchC
         __stcg(k.root_exp + at, e_sum);
       }
     }
+    __syncthreads();  // tile, colmax and cur_e are settled before the next op streams into shared memory
   }
 }
 

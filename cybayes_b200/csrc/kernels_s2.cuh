@@ -82,17 +82,26 @@ template <int V> struct VecD;
 template <> struct VecD<1> {
   double v[1];
   __device__ __forceinline__ void load(const double* p) { v[0] = __ldcg(p); }
+  __device__ __forceinline__ void load_ca(const double* p) { v[0] = __ldca(p); }
   __device__ __forceinline__ void store(double* p) const { __stcg(p, v[0]); }
 };
 template <> struct VecD<2> {
   double v[2];
   __device__ __forceinline__ void load(const double* p) { const double2 t = ld_cg2(p); v[0] = t.x; v[1] = t.y; }
+  __device__ __forceinline__ void load_ca(const double* p) {
+    const double2 t = __ldca(reinterpret_cast<const double2*>(p)); v[0] = t.x; v[1] = t.y;
+  }
   __device__ __forceinline__ void store(double* p) const { st_cg2(p, make_double2(v[0], v[1])); }
 };
 template <int V> __device__ __forceinline__ void load_ints(const int32_t* p, int (&e)[V]);
 template <> __device__ __forceinline__ void load_ints<1>(const int32_t* p, int (&e)[1]) { e[0] = __ldcg(p); }
 template <> __device__ __forceinline__ void load_ints<2>(const int32_t* p, int (&e)[2]) {
   const int2 t = __ldcg(reinterpret_cast<const int2*>(p)); e[0] = t.x; e[1] = t.y;
+}
+template <int V> __device__ __forceinline__ void load_ints_ca(const int32_t* p, int (&e)[V]);
+template <> __device__ __forceinline__ void load_ints_ca<1>(const int32_t* p, int (&e)[1]) { e[0] = __ldca(p); }
+template <> __device__ __forceinline__ void load_ints_ca<2>(const int32_t* p, int (&e)[2]) {
+  const int2 t = __ldca(reinterpret_cast<const int2*>(p)); e[0] = t.x; e[1] = t.y;
 }
 template <int V> __device__ __forceinline__ void store_ints(int32_t* p, const int (&e)[V]);
 template <> __device__ __forceinline__ void store_ints<1>(int32_t* p, const int (&e)[1]) { __stcg(p, e[0]); }
