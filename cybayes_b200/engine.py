@@ -96,10 +96,12 @@ class Engine(SlotPool):
         self._pending = []  # queued cb_pmat_build jobs
         self._lnl = np.zeros(1)
         self._snap = C.c_int(-1)
-        self._finalizer = weakref.finalize(self, Engine._destroy, lib, ctx)
+        self._state = {"alive": True}
+        self._finalizer = weakref.finalize(self, Engine._destroy, lib, ctx, self._state)
 
     @staticmethod
-    def _destroy(lib, ctx):
+    def _destroy(lib, ctx, state):
+        state["alive"] = False   # handles that outlive the context (caches, slot blocks) become no-ops
         lib.cb_destroy(ctx)
 
     def close(self):
@@ -195,7 +197,7 @@ class Engine(SlotPool):
         check(self._lib.cb_snapshot_retain(self._ctx, int(snap)))
 
     def release_snapshot(self, snap):
-        if self._ctx is not None:
+        if self._ctx is not None and self._state["alive"]:
             check(self._lib.cb_snapshot_release(self._ctx, int(snap)))
 
     def read_partial(self, snap, node, with_scale=False):
