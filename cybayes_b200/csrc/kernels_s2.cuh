@@ -143,7 +143,7 @@ __device__ __forceinline__ void fetch_codes(const S2Stage& op, int code_bytes, i
 
 __host__ __device__ inline size_t s2_smem_bytes(int ops, int C) {
   const int n = ops < S2_STAGE_OPS ? ops : S2_STAGE_OPS;
-  return (size_t)n * (sizeof(S2Stage) + (size_t)8 * C * sizeof(double));
+  return (size_t)n * (sizeof(S2Stage) + (size_t)16 * C * sizeof(double));
 }
 
 template <int C, int V, int THREADS, int MINB>
@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
   const int nops = rg.end - rg.begin;
   const int n_stage = min(nops, S2_STAGE_OPS);
   S2Stage* st = reinterpret_cast<S2Stage*>(s2_smem);
-  double2* p_stage = reinterpret_cast<double2*>(s2_smem + (size_t)n_stage * sizeof(S2Stage));  // [op][child][C][row] = (Pi0, Pi1)
+  // per (op, child): 8*C doubles.  Internal child: [C][row] pairs (Pi0, Pi1) in the first half.
+  // Tip child: [C][row][4] = (Pi0, Pi1, Pi0 + Pi1, -): the edge's contribution looked up by state code.
+  double* p_stage = reinterpret_cast<double*>(s2_smem + (size_t)n_stage * sizeof(S2Stage));
 
   const int64_t P = k.n_sites;
   const int64_t tile0 = (int64_t)blockIdx.x * (THREADS * V);
@@ -187,12 +189,20 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
       r.is_root = op->is_root; r.pad_ = 0;
       st[o] = r;
     }
-    // ... their P matrices ...
-    {
-      double* ps = reinterpret_cast<double*>(p_stage);
-      for (int idx = threadIdx.x; idx < (o1 - o0) * 8 * C; idx += THREADS) {
-        const int e = idx & 3, c = (idx >> 2) % C, ch = (idx / (4 * C)) & 1, o = idx / (8 * C);
-        ps[idx] = __ldg(k.pmats + (int64_t)k.ops[rg.begin + o0 + o].pslot[ch][c] * 4 + e);
+    // ... their P matrices (tip children get a 3-entry lookup per row: state 0, state 1, missing) ...
+    for (int idx = threadIdx.x; idx < (o1 - o0) * 4 * C; idx += THREADS) {
+      const int i = idx & 1, c = (idx >> 1) % C, ch = (idx / (2 * C)) & 1, o = idx / (4 * C);
+      const OpDesc* __restrict__ op = k.ops + rg.begin + o0 + o;
+      const double2 pr = __ldg(reinterpret_cast<const double2*>(k.pmats + (int64_t)op->pslot[ch][c] * 4) + i);
+      double* base = p_stage + (size_t)(o * 2 + ch) * 8 * C;
+      if (op->kind[ch] == SRC_TIP) {
+        double* t = base + (c * 2 + i) * 4;
+        t[0] = pr.x;
+        t[1] = pr.y;
+        t[2] = fma(pr.y, 1.0, pr.x * 1.0);  // all-ones column: P[i][0] + P[i][1], as the FMA chain gives it
+        t[3] = 0.0;
+      } else {
+        reinterpret_cast<double2*>(base)[c * 2 + i] = pr;
       }
     }
     // ... and pull this tile's tip codes of the NEXT chunk towards L2 while this chunk computes
@@ -232,7 +242,8 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         const int kind = op.kind[ch];
-        const double2* pm = p_stage + ((o - o0) * 2 + ch) * C * 2;  // (P[i][0], P[i][1]) broadcasts
+        const double* pbase = p_stage + (size_t)((o - o0) * 2 + ch) * 8 * C;
+        const double2* pm = reinterpret_cast<const double2*>(pbase);  // (P[i][0], P[i][1]) broadcasts
         // v[i] = P[i][0] L[0] + P[i][1] L[1]; first child initialises `out`, second multiplies into it
 #define CB_S2_APPLY(L0, L1)                                                   \
   _Pragma("unroll") for (int c = 0; c < C; ++c) {                            \
@@ -261,14 +272,19 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
           CB_S2_APPLY(L[c][0].v[v], L[c][1].v[v])
 #pragma unroll
           for (int v = 0; v < V; ++v) e_in[v] += se[v];
-        } else {  // tip: state code -> 0/1 indicator column (utils.pyx:99-111); 2 = '?' / '-' / '0/1'
-          double t0[V], t1[V];
+        } else {  // tip: state code 0 / 1 / 2 ('?', '-', '0/1') selects the staged contribution of this edge
+          // (= the FMA chain over the 0/1 indicator column of utils.pyx:99-111, bit for bit)
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
-            t0[v] = (code[ch][v] != 1u) ? 1.0 : 0.0;
-            t1[v] = (code[ch][v] != 0u) ? 1.0 : 0.0;
+          for (int c = 0; c < C; ++c) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+#pragma unroll
+              for (int v = 0; v < V; ++v) {
+                const double x = pbase[(c * 2 + i) * 4 + min(code[ch][v], 2u)];
+                if (ch == 0) out[c][i].v[v] = x; else out[c][i].v[v] *= x;
+              }
+            }
           }
-          CB_S2_APPLY(t0[v], t1[v])
         }
 #undef CB_S2_APPLY
       }
