@@ -15,6 +15,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -46,6 +48,21 @@ static int fail(const char* fmt, ...) {
   do {                                \
     if (!(cond)) return fail(__VA_ARGS__); \
   } while (0)
+
+
+// No C++ exception may cross the C ABI: every entry point that allocates runs under this guard.
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    return fail("out of host memory");
+  } catch (const std::exception& e) {
+    return fail("internal error: %s", e.what());
+  } catch (...) {
+    return fail("internal error: unknown exception");
+  }
+}
 
 // ------------------------------------------------------------------------------- NCCL (dlopen)
 struct NcclId { char internal[128]; };
@@ -166,7 +183,11 @@ extern "C" int cb_device_count(int* out) {
   return 0;
 }
 
+static int create_impl(int device, cb_ctx** out);
 extern "C" int cb_create(int device, cb_ctx** out) {
+  return guarded([&] { return create_impl(device, out); });
+}
+static int create_impl(int device, cb_ctx** out) {
   REQUIRE(out, "null argument");
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -284,9 +305,15 @@ static int ensure_scratch(cb_ctx* c, size_t bytes) {
   return 0;
 }
 
+static int set_tips_impl(cb_ctx* c, int n_taxa, int64_t n_sites, int n_states, int n_cats, const void* codes,
+                         int code_bytes, const double* amb_sets, int n_amb, const double* weights);
 extern "C" int cb_set_tips(cb_ctx* c, int n_taxa, int64_t n_sites, int n_states, int n_cats,
                            const void* codes, int code_bytes, const double* amb_sets, int n_amb,
                            const double* weights) {
+  return guarded([&] { return set_tips_impl(c, n_taxa, n_sites, n_states, n_cats, codes, code_bytes, amb_sets, n_amb, weights); });
+}
+static int set_tips_impl(cb_ctx* c, int n_taxa, int64_t n_sites, int n_states, int n_cats, const void* codes,
+                         int code_bytes, const double* amb_sets, int n_amb, const double* weights) {
   REQUIRE(c && codes, "null argument");
   REQUIRE(n_taxa >= 2 && n_sites >= 1 && n_states >= 2, "bad alignment shape %d x %lld x %d", n_taxa,
           (long long)n_sites, n_states);
@@ -471,7 +498,11 @@ extern "C" int cb_snapshot_release(cb_ctx* c, int s) {
   return 0;
 }
 
+static int snapshot_read_impl(cb_ctx* c, int s, int node, double* out, int32_t* scale_out);
 extern "C" int cb_snapshot_read(cb_ctx* c, int s, int node, double* out, int32_t* scale_out) {
+  return guarded([&] { return snapshot_read_impl(c, s, node, out, scale_out); });
+}
+static int snapshot_read_impl(cb_ctx* c, int s, int node, double* out, int32_t* scale_out) {
   REQUIRE(c && out && snapshot_valid(c, s), "invalid snapshot %d", s);
   const Snapshot& sn = c->snaps[s];
   REQUIRE(node >= 0 && node < (int)sn.buf_of_node.size() && sn.buf_of_node[node] >= 0,
@@ -991,13 +1022,13 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
 extern "C" int cb_eval(cb_ctx* c, int snapshot_in, int n_ops, const int32_t* nodes, const int32_t* children,
                        const int32_t* pslots, const double* pi, int flags, int* snapshot_out, double* lnl_out) {
   const int32_t offsets[2] = {0, n_ops};
-  return eval_impl(c, snapshot_in, 1, offsets, nodes, children, pslots, pi, flags, snapshot_out, lnl_out);
+  return guarded([&] { return eval_impl(c, snapshot_in, 1, offsets, nodes, children, pslots, pi, flags, snapshot_out, lnl_out); });
 }
 
 extern "C" int cb_eval_batch(cb_ctx* c, int snapshot_in, int n_batch, const int32_t* op_offsets, const int32_t* nodes,
                              const int32_t* children, const int32_t* pslots, const double* pi, double* lnl_out) {
   REQUIRE(n_batch >= 1, "empty batch");
-  return eval_impl(c, snapshot_in, n_batch, op_offsets, nodes, children, pslots, pi, 0, nullptr, lnl_out);
+  return guarded([&] { return eval_impl(c, snapshot_in, n_batch, op_offsets, nodes, children, pslots, pi, 0, nullptr, lnl_out); });
 }
 
 extern "C" int cb_result_wait(cb_ctx* c, double* lnl_out) {

@@ -69,9 +69,54 @@ def engine_for(ll_mats, n_cats):
         pat, w, smap = compress_patterns(codes)
         if pat.shape[1] < codes.shape[1]:
             codes, weights, site_map = pat, w, smap
+    rank, world = _shard_rank()
+    if world > 1:
+        # site-pattern sharding: this process (one per GPU) keeps a contiguous slice of the patterns; the
+        # library all-reduces the scalar lnL over NCCL, so every rank sees the same number
+        from .synthetic import shard_bounds
+        lo, hi = shard_bounds(codes.shape[1], rank, world, 64)
+        if hi <= lo:
+            raise ValueError(f"alignment has too few patterns ({codes.shape[1]}) to shard over {world} GPUs")
+        codes = np.ascontiguousarray(codes[:, lo:hi])
+        weights = None if weights is None else np.ascontiguousarray(weights[lo:hi])
+        site_map = None  # per-site read-back of partials is a single-GPU debugging aid
     eng = _engine_factory(codes, S, n_cats, amb, weights)
+    if world > 1:
+        eng.comm_init(_nccl_id(eng, rank, f"{S}x{n_cats}x{len(_engines)}"), rank, world)
     _engines[key] = (ll_mats, eng, site_map)
     return eng, site_map
+
+
+def _shard_rank():
+    """(rank, world) when CYBAYES_SHARD=1 and the process was started by torchrun / mpirun-style env."""
+    if os.environ.get("CYBAYES_SHARD", "0") != "1":
+        return 0, 1
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def _nccl_id(eng, rank, tag):
+    """NCCL unique id made by rank 0 and handed to the other ranks through a file (no torch needed):
+    CYBAYES_NCCL_ID_DIR (default: the system temp dir) / cybayes_nccl_<MASTER_PORT>_<tag>.id"""
+    import tempfile
+    import time
+    d = os.environ.get("CYBAYES_NCCL_ID_DIR", tempfile.gettempdir())
+    # all ranks of one launch share the parent (the torchrun agent): its pid keeps launches apart
+    path = os.path.join(d, f"cybayes_nccl_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_{tag}.id")
+    if rank == 0:
+        import atexit
+        uid = eng.nccl_unique_id()
+        with open(path + ".tmp", "wb") as fh:
+            fh.write(uid)
+        os.replace(path + ".tmp", path)
+        atexit.register(lambda: os.path.exists(path) and os.remove(path))
+        return uid
+    t0 = time.time()
+    while not os.path.exists(path):
+        if time.time() - t0 > 120:
+            raise TimeoutError(f"rank 0 never published {path}")
+        time.sleep(0.01)
+    with open(path, "rb") as fh:
+        return fh.read()
 
 
 def _default_engine(n_cats=None):

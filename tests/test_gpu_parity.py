@@ -135,7 +135,8 @@ def _oracle_leaves(codes, S, amb):
     return {t + 1: np.ascontiguousarray(table[codes[t].astype(np.int64)].T) for t in range(codes.shape[0])}
 
 
-@pytest.mark.parametrize("S,n_taxa,n_sites,model", [(2, 12, 333, "F81"), (2, 40, 1000, "GTR"), (4, 9, 65, "GTR"),
+@pytest.mark.parametrize("S,n_taxa,n_sites,model", [(2, 2, 70, "F81"), (5, 3, 10, "GTR"), (2, 12, 333, "F81"),
+                                                    (2, 40, 1000, "GTR"), (4, 9, 65, "GTR"), (40, 7, 90, "GTR"),
                                                     (6, 17, 200, "F81"), (23, 14, 129, "JC"), (47, 10, 64, "GTR"),
                                                     (64, 8, 100, "GTR"), (130, 6, 40, "F81")])
 def test_random_inputs_vs_oracle(S, n_taxa, n_sites, model, gpu_backend):
