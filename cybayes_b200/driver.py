@@ -25,6 +25,7 @@ import numpy as np
 
 from . import config, utils
 from .ML_gamma import cache_matML, matML
+from .subst import get_edge_transition_mats
 from .mcmc_gamma import (adjlist2newickBL, adjlist2nodes_dict, adjlist2reverse_nodes_dict, externalSPR,
                          get_edge_transition_mat, get_path2root, get_prob_t, get_siterates, mvDualSlider,
                          node_slider, rooted_NNI, scale_alpha, scale_edge, state_init)
@@ -161,11 +162,12 @@ def run_chain(input_file, model, n_gen, thin, data_type, output_file, reader=Non
             site_rates = get_siterates(new_param)
 
         if param == "bl":
-            for k, rate in enumerate(site_rates):
+            new_p = iter(get_edge_transition_mats(pi_prop, rates_prop,
+                                                  [tree_prop[e] * rate for rate in site_rates for e in changed]))
+            for k in range(len(site_rates)):
                 for e in changed:
                     undo.append((k, e, tmats[k][e]))
-                for e in changed:
-                    tmats[k][e] = get_edge_transition_mat(pi_prop, rates_prop, tree_prop[e] * rate)
+                    tmats[k][e] = next(new_p)
             proposed_ll, proposed_cache = cache_matML(pi_prop, root, leaves, cache, dirty, state["postorder"], tmats,
                                                       n_sites, n_taxa, n_cats)
         elif name == "rooted_NNI":

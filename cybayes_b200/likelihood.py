@@ -18,7 +18,7 @@ import numpy as np
 from . import config, subst
 from .alignment import LeafMatrices, compress_patterns
 from .engine import Engine
-from .subst import PMatTable, table_from_host
+from .subst import PMatTable
 
 # ---------------------------------------------------------------------------- engines
 _engines = {}  # (id(ll_mats), n_cats) -> (ll_mats, Engine, site_to_pattern or None)
@@ -198,17 +198,31 @@ def _plan_for(edges):
 
 
 def _slot_matrix(engine, tmats, edge_keys):
-    """(n_edges, C) int32 P-slot table for the ops' edges."""
+    """(n_edges, C) int32 P-slot table for the ops' edges.  Device tables are looked up; reference-style
+    host dicts of ndarrays are uploaded (host buffers -> one H2D copy per category) in op order."""
     cols = []
-    getter = itemgetter(*edge_keys) if len(edge_keys) > 1 else None
+    getter = itemgetter(*edge_keys) if len(edge_keys) > 1 else (lambda d: (d[edge_keys[0]],))
     keep = []
+    n = len(edge_keys)
+    S = engine.n_states
     for t in tmats:
-        if not isinstance(t, PMatTable):
-            t = table_from_host(engine, t)   # reference-style host matrices: upload (host buffers)
-            keep.append(t)
-        elif t.engine is not engine:
-            raise ValueError("transition matrices belong to a different alignment")
-        cols.append(getter(t._slots) if getter else (t._slots[edge_keys[0]],))
+        if isinstance(t, PMatTable):
+            if t.engine is not engine:
+                raise ValueError("transition matrices belong to a different alignment")
+            cols.append(getter(t._slots))
+            continue
+        vals = getter(t)
+        try:   # fastest way to gather thousands of small (S, S) arrays into one buffer
+            mats = np.concatenate(vals)
+            if mats.dtype != np.float64 or mats.shape != (n * S, S):
+                raise ValueError
+        except (ValueError, TypeError):
+            mats = np.array([np.asarray(v, dtype=np.float64) for v in vals])
+        block = engine.alloc_slots(n)
+        slots = np.arange(block.base, block.base + n, dtype=np.int32)
+        engine.upload_pmats(slots, mats)
+        keep.append(block)
+        cols.append(slots)
     return np.ascontiguousarray(np.array(cols, dtype=np.int32).T), keep
 
 

@@ -129,7 +129,13 @@ def table_from_host(engine, mapping):
     """Upload a reference-style ``{edge: ndarray}`` dict (host buffers) into a PMatTable."""
     edges = list(mapping.keys())
     block = engine.alloc_slots(len(edges))
-    mats = np.array(list(mapping.values()), dtype=np.float64)
+    vals = list(mapping.values())
+    try:   # fastest way to gather thousands of small (S, S) arrays into one buffer
+        mats = np.concatenate(vals)
+        if mats.dtype != np.float64 or mats.shape != (len(vals) * engine.n_states, engine.n_states):
+            raise ValueError
+    except (ValueError, TypeError):
+        mats = np.array([np.asarray(v, dtype=np.float64) for v in vals])
     engine.upload_pmats(np.arange(block.base, block.base + block.n, dtype=np.int32), mats)
     return PMatTable(engine, edges, block)
 
@@ -223,6 +229,21 @@ def get_edge_transition_mat(pi, rates, d, n_cats=None):
     block = engine.alloc_slots(1)
     _queue(engine, model, config.IN_DTYPE == "bin", pi, rates, [block.base], [float(d)], config.NORM_BETA)
     return PMatrix(engine, block.base, block)
+
+
+def get_edge_transition_mats(pi, rates, ds, n_cats=None):
+    """[P(d) for d in ds] in one queue entry (one slot block): what a branch move needs for all rate
+    categories (and both branches of a node slide).  Same matrices as get_edge_transition_mat."""
+    engine = _engine(n_cats)
+    model = config.MODEL
+    if model == "F81":
+        config.NORM_BETA = f81_beta(np.asarray(pi))
+    n = len(ds)
+    block = engine.alloc_slots(n)
+    base = block.base
+    _queue(engine, model, config.IN_DTYPE == "bin", pi, rates, list(range(base, base + n)), [float(d) for d in ds],
+           config.NORM_BETA)
+    return [PMatrix(engine, base + i, block) for i in range(n)]
 
 
 def get_siterates(alpha):
