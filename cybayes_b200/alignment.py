@@ -80,9 +80,28 @@ def encode_tokens(rows, alphabet):
     for m in MISSING:
         lookup[m] = S
     wide = np.empty((n_taxa, n_sites), dtype=np.int64)
+    # single-character alphabets (binary / readMultiPhy rows given as strings): one table lookup per row
+    lut = None
+    if all(len(a) == 1 and ord(a) < 256 for a in alphabet):
+        lut = np.full(256, -1, dtype=np.int64)
+        for a, i in index.items():
+            lut[ord(a)] = i
+        for m in MISSING:
+            lut[ord(m)] = S
     for t, toks in enumerate(rows):
         if len(toks) != n_sites:
             raise ValueError(f"taxon {t + 1}: {len(toks)} characters, expected {n_sites}")
+        if lut is not None:
+            codes_row = None
+            try:
+                text = toks if isinstance(toks, str) else "".join(toks)
+                if len(text) == n_sites:  # every token is one character
+                    codes_row = lut[np.frombuffer(text.encode("latin-1"), dtype=np.uint8)]
+            except (UnicodeEncodeError, TypeError):
+                codes_row = None
+            if codes_row is not None and (codes_row >= 0).all():
+                wide[t] = codes_row
+                continue
         try:
             wide[t] = [lookup[tok] for tok in toks]
         except KeyError:
@@ -154,7 +173,7 @@ def _read(fname, mode):
                         chars = list(vec)
                     seen = vec
             taxon = taxon.replace(" ", "")
-            for ch in seen:
+            for ch in dict.fromkeys(seen):  # distinct symbols in order of first appearance
                 if ch not in alphabet and ch not in MISSING:
                     alphabet.append(ch)
             site_dict[taxon] = chars

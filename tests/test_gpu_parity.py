@@ -404,3 +404,54 @@ def test_unmodified_non_gamma_driver_runs_on_the_engine(name, fname, model, dtyp
                                             "-n", str(n_gen), "-t", "1", "-d", dtype, "-o", str(tmp_path / "ng")],
                                monkeypatch, capsys)
     check_nongamma_trace(out, name, REL_CLOSED)
+
+
+@pytest.mark.parametrize("name", ["phon_ringe_F81", "narrow_F81", "ielex_multistate_F81"])
+def test_batched_nni_scoring(name, golden_cases, gpu_backend):
+    """every NNI neighbour of the start tree scored against one cache in ONE launch
+    (ML_gamma.score_proposals): bit-identical to cache_matML per candidate, and equal to the oracle's
+    dirty-path likelihood (ML_gamma.pyx:83-118) for a sample of candidates."""
+    from cybayes_b200.mcmc_gamma import (adjlist2nodes_dict, adjlist2reverse_nodes_dict, get_path2root, get_prob_t,
+                                         postorder)
+    from cybayes_b200.ML_gamma import cache_matML, matML, score_proposals
+    case = golden_cases[name]
+    config = _setup_case(case)
+    tree, pi, rates, edges, site_rates = golden_io.case_state(case)
+    if rates is None:
+        rates = np.ones(1)
+    tmats = [get_prob_t(pi, tree, rates, r) for r in site_rates]
+    args = (config.N_SITES, config.N_TAXA, config.N_CATS)
+    root, N = case["root"], case["n_taxa"]
+    lnl, cache = matML(pi, root, config.LEAF_LLMAT, edges, tmats, *args)
+    kids = adjlist2nodes_dict(tree)
+    proposals, trees = [], []
+    for (a, b) in list(tree):
+        if b <= N:
+            continue
+        src = kids[a][1] if kids[a][0] == b else kids[a][0]
+        for tgt in kids[b]:
+            t2 = dict(tree)
+            sbl, tbl = t2.pop((a, src)), t2.pop((b, tgt))
+            t2[a, tgt], t2[b, src] = tbl, sbl
+            tm = []
+            for k in range(config.N_CATS):
+                tk = tmats[k].copy()
+                tk[a, tgt], tk[b, src] = tk[b, tgt], tk[a, src]
+                tm.append(tk)
+            order = postorder(adjlist2nodes_dict(t2), root)[::-1]
+            dirty = [b] + get_path2root(adjlist2reverse_nodes_dict(t2), b, root)
+            proposals.append((dirty, order, tm))
+            trees.append(t2)
+    assert len(proposals) == 2 * (N - 2)
+    batch = score_proposals(pi, root, config.LEAF_LLMAT, cache, proposals)
+    single = [cache_matML(pi, root, config.LEAF_LLMAT, cache, d, o, tm, *args)[0] for d, o, tm in proposals]
+    assert batch.tolist() == [float(x) for x in single]
+    assert len(set(batch.tolist())) > N // 2            # the candidates really differ
+    # oracle: full likelihood of the rearranged tree (same branch lengths moved with the subtrees)
+    _, _, _, _, ll, _, n_sites = oracle.read_phylip(golden_io.data_path(case), case["reader"])
+    for idx in range(0, len(proposals), max(1, len(proposals) // 5)):
+        t2 = trees[idx]
+        tm_o = [oracle.prob_t(case["model"], case["dtype"] == "bin", pi, t2, rates, r, beta=case["norm_beta"])
+                for r in site_rates]
+        want = oracle.mat_ml(pi, root, ll, proposals[idx][1], tm_o, n_sites, N)[0]
+        assert abs(batch[idx] - want) <= 1e-11 * abs(want), (idx, batch[idx], want)
