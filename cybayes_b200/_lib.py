@@ -46,6 +46,7 @@ SIGNATURES = {
 
 CB_MODEL_JC, CB_MODEL_F81, CB_MODEL_F81_BINARY, CB_MODEL_GTR_EIG = 0, 1, 2, 3
 CB_EVAL_WANT_SNAPSHOT, CB_EVAL_STORE_ROOT, CB_EVAL_NO_SYNC, CB_EVAL_FORCE_LEVELS, CB_EVAL_FORCE_WALK = 1, 2, 4, 8, 16
+CB_EVAL_NO_FOLD = 32
 
 _lib = None
 

@@ -5,21 +5,32 @@
 
 namespace cb {
 
-enum SrcKind : int32_t { SRC_TIP = 0, SRC_BUFFER = 1, SRC_CARRIED = 2 };
+// SRC_CHERRY (2-state family only): the child is a "cherry" -- an internal node whose two children are
+// tips.  Its partial has only 3 x 3 possible values per rate category (state code of either tip: 0, 1,
+// missing), so it is never computed per site, stored or read: the parent looks its contribution up.
+enum SrcKind : int32_t { SRC_TIP = 0, SRC_BUFFER = 1, SRC_CARRIED = 2, SRC_CHERRY = 3 };
+
+constexpr int CB_S2_MAX_CATS = 4;            // rate categories of the 2-state kernels (1 or 4)
+constexpr int32_t CB_LIB_SLOT = 1 << 30;     // P-slot ids with this bit address the library's own pool
 
 // One node operation: L_node = (P_a . L_a) * (P_b . L_b), ML_gamma.pyx:24-36.
-// 128 bytes, read by every block of a launch through the read-only path.
+// 256 bytes, read by every block of a launch through the read-only path.
 struct OpDesc {
   double* dst;                  // [C][S][P] or nullptr (not stored)
   int32_t* dst_scale;           // [P] (2-state family) or [C][P] (general family)
-  const void* src[2];           // tip code row, partial buffer, or nullptr when carried
+  const void* src[2];           // tip code row, partial buffer, or nullptr when carried / cherry
   const int32_t* src_scale[2];  // nullptr for tips
   int32_t kind[2];              // SrcKind
   int32_t pslot[2][CB_MAX_CATS];
   int32_t is_root;
   int32_t pad_;
+  // folded cherry children (kind == SRC_CHERRY)
+  const void* ctip[2][2];                  // code rows of the cherry's two tips
+  int32_t cslot[2][2][CB_S2_MAX_CATS];     // P slots of the cherry's two tip edges, per category
+  int32_t crec_out[2];                     // library record that must keep a copy of those P, or -1
+  int32_t pad2_[6];
 };
-static_assert(sizeof(OpDesc) == 128, "OpDesc must stay 128 bytes");
+static_assert(sizeof(OpDesc) == 256, "OpDesc must stay 256 bytes");
 
 // A block walks ops [begin, end) in order for its site tile; results of a root op go to
 // results[out_index].
@@ -31,6 +42,7 @@ struct LaunchConst {
   const OpDesc* ops;
   const RangeDesc* ranges;
   const double* pmats;     // slot pool, S*S doubles per slot
+  double* pmats_lib;       // library-owned slots (copies of the P matrices of folded cherries)
   const double* weights;   // [P]
   const double* pi;        // [S]
   const double* amb;       // [n_amb][S] 0/1

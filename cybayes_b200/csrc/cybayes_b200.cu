@@ -102,7 +102,14 @@ struct Buffer {
   int refs = 0;
 };
 struct Snapshot {
-  std::vector<int32_t> buf_of_node;  // index by node id; -1 = absent
+  std::vector<int32_t> buf_of_node;     // index by node id; -1 = absent
+  std::vector<int32_t> cherry_of_node;  // 2-state family: record of a folded cherry (never materialised), or -1
+  int refs = 0;
+};
+// A folded cherry kept by a snapshot: its two tips and, in the library's own P pool at slots
+// [rec * 2C, (rec + 1) * 2C), copies of the P matrices of its two tip edges (tip 0: C slots, tip 1: C slots).
+struct CherryRec {
+  int32_t tip[2] = {0, 0};
   int refs = 0;
 };
 
@@ -131,6 +138,10 @@ struct cb_ctx {
   size_t buffer_bytes = 0;
   std::vector<Snapshot> snaps;
   std::vector<int> free_snaps;
+  std::vector<CherryRec> recs;
+  std::vector<int> free_recs;
+  double* d_pmats_lib = nullptr;
+  int lib_cap = 0;  // records the library pool can hold
   // staging
   OpDesc* h_ops = nullptr;
   OpDesc* d_ops = nullptr;
@@ -222,6 +233,11 @@ static void free_alignment(cb_ctx* c) {
   c->free_buffers.clear();
   c->snaps.clear();
   c->free_snaps.clear();
+  c->recs.clear();
+  c->free_recs.clear();
+  if (c->d_pmats_lib) dev_free(c, c->d_pmats_lib, (size_t)c->lib_cap * 2 * c->n_cats * c->n_states * c->n_states * 8);
+  c->d_pmats_lib = nullptr;
+  c->lib_cap = 0;
   if (c->d_codes) dev_free(c, c->d_codes, (size_t)c->n_taxa * c->P * c->code_bytes);
   if (c->d_weights) dev_free(c, c->d_weights, (size_t)c->P * 8);
   if (c->d_amb) dev_free(c, c->d_amb, (size_t)std::max(1, c->n_amb) * c->n_states * 8);
@@ -480,6 +496,40 @@ static void buffer_release(cb_ctx* c, int b) {
   if (b < 0) return;
   if (--c->buffers[b].refs == 0) c->free_buffers.push_back(b);
 }
+static int rec_acquire(cb_ctx* c, int tip0, int tip1, int* out) {
+  if (!c->free_recs.empty()) {
+    *out = c->free_recs.back();
+    c->free_recs.pop_back();
+  } else {
+    c->recs.emplace_back();
+    *out = (int)c->recs.size() - 1;
+  }
+  c->recs[*out].tip[0] = tip0;
+  c->recs[*out].tip[1] = tip1;
+  c->recs[*out].refs = 1;
+  return 0;
+}
+static void rec_release(cb_ctx* c, int r) {
+  if (r < 0) return;
+  if (--c->recs[r].refs == 0) c->free_recs.push_back(r);
+}
+// the library's P pool must hold every record that exists (old contents are kept when it grows)
+static int ensure_lib_pool(cb_ctx* c) {
+  const int need = (int)c->recs.size();
+  if (need <= c->lib_cap) return 0;
+  const int cap = std::max(need, std::max(1024, c->lib_cap * 2));
+  const size_t per = (size_t)2 * c->n_cats * c->n_states * c->n_states * 8;
+  double* nd = nullptr;
+  if (dev_alloc(c, (void**)&nd, (size_t)cap * per)) return 1;
+  if (c->d_pmats_lib) {
+    CU(cudaMemcpyAsync(nd, c->d_pmats_lib, (size_t)c->lib_cap * per, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    dev_free(c, c->d_pmats_lib, (size_t)c->lib_cap * per);
+  }
+  c->d_pmats_lib = nd;
+  c->lib_cap = cap;
+  return 0;
+}
 static bool snapshot_valid(cb_ctx* c, int s) {
   return s >= 0 && s < (int)c->snaps.size() && c->snaps[s].refs > 0;
 }
@@ -492,7 +542,9 @@ extern "C" int cb_snapshot_release(cb_ctx* c, int s) {
   REQUIRE(c && snapshot_valid(c, s), "invalid snapshot %d", s);
   if (--c->snaps[s].refs == 0) {
     for (int32_t b : c->snaps[s].buf_of_node) buffer_release(c, b);
+    for (int32_t r : c->snaps[s].cherry_of_node) rec_release(c, r);
     c->snaps[s].buf_of_node.clear();
+    c->snaps[s].cherry_of_node.clear();
     c->free_snaps.push_back(s);
   }
   return 0;
@@ -502,13 +554,20 @@ static int snapshot_read_impl(cb_ctx* c, int s, int node, double* out, int32_t* 
 extern "C" int cb_snapshot_read(cb_ctx* c, int s, int node, double* out, int32_t* scale_out) {
   return guarded([&] { return snapshot_read_impl(c, s, node, out, scale_out); });
 }
+static int materialize_cherry(cb_ctx* c, int rec, int* buf_out);
 static int snapshot_read_impl(cb_ctx* c, int s, int node, double* out, int32_t* scale_out) {
   REQUIRE(c && out && snapshot_valid(c, s), "invalid snapshot %d", s);
   const Snapshot& sn = c->snaps[s];
-  REQUIRE(node >= 0 && node < (int)sn.buf_of_node.size() && sn.buf_of_node[node] >= 0,
-          "node %d is not in snapshot %d", node, s);
+  REQUIRE(node >= 0 && node < (int)sn.buf_of_node.size(), "node %d is not in snapshot %d", node, s);
   CU(cudaSetDevice(c->device));
-  const Buffer& b = c->buffers[sn.buf_of_node[node]];
+  int bidx = sn.buf_of_node[node], tmp_buf = -1;
+  if (bidx < 0 && node < (int)sn.cherry_of_node.size() && sn.cherry_of_node[node] >= 0) {
+    // a folded cherry has no stored partial: compute it now, from the P copies the snapshot keeps
+    if (materialize_cherry(c, sn.cherry_of_node[node], &tmp_buf)) return 1;
+    bidx = tmp_buf;
+  }
+  REQUIRE(bidx >= 0, "node %d is not in snapshot %d", node, s);
+  const Buffer& b = c->buffers[bidx];
   const int C = c->n_cats, S = c->n_states;
   const int64_t P = c->P, n = c->n_sites;
   std::vector<double> tmp((size_t)C * S * P);
@@ -543,6 +602,7 @@ static int snapshot_read_impl(cb_ctx* c, int s, int node, double* out, int32_t* 
       }
     }
   }
+  if (tmp_buf >= 0) buffer_release(c, tmp_buf);
   return 0;
 }
 
@@ -599,6 +659,7 @@ static LaunchConst make_const(cb_ctx* c) {
   k.ops = c->d_ops;
   k.ranges = c->d_ranges;
   k.pmats = c->d_pmats;
+  k.pmats_lib = c->d_pmats_lib;
   k.weights = c->d_weights;
   k.pi = c->d_pi;
   k.amb = c->d_amb;
@@ -675,6 +736,34 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
   return 0;
 }
 
+// Compute the partial of a folded cherry into a fresh buffer (debug / read-back path): one ordinary op
+// with two tip children whose P matrices come from the library's pool.
+static int materialize_cherry(cb_ctx* c, int rec, int* buf_out) {
+  REQUIRE(c->family_s2 && rec >= 0 && rec < (int)c->recs.size(), "bad cherry record %d", rec);
+  if (ensure_staging(c, 1, 1, 1)) return 1;
+  CU(cudaStreamSynchronize(c->stream));
+  int bi;
+  if (buffer_acquire(c, &bi)) return 1;
+  OpDesc& op = c->h_ops[0];
+  memset(&op, 0, sizeof op);
+  op.dst = c->buffers[bi].data;
+  op.dst_scale = c->buffers[bi].scale;
+  for (int kx = 0; kx < 2; ++kx) {
+    op.kind[kx] = SRC_TIP;
+    op.src[kx] = (const char*)c->d_codes + (size_t)(c->recs[rec].tip[kx] - 1) * c->P * c->code_bytes;
+    for (int q = 0; q < c->n_cats; ++q) op.pslot[kx][q] = CB_LIB_SLOT | (rec * 2 * c->n_cats + kx * c->n_cats + q);
+    op.crec_out[kx] = -1;
+  }
+  c->h_ranges[0] = RangeDesc{0, 1, -1, 0};
+  CU(cudaMemcpyAsync(c->d_ops, c->h_ops, sizeof(OpDesc), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_ranges, c->h_ranges, sizeof(RangeDesc), cudaMemcpyHostToDevice, c->stream));
+  const LaunchConst k = make_const(c);
+  if (launch_ranges(c, k, 0, 1, 1)) return 1;
+  CU(cudaStreamSynchronize(c->stream));
+  *buf_out = bi;
+  return 0;
+}
+
 // Shared implementation of cb_eval (n_lists = 1) and cb_eval_batch.
 //
 // Schedules (all run the same per-node arithmetic, so results are bit-identical):
@@ -689,15 +778,60 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
 //          small alignments where a site tile alone cannot fill the GPU.
 enum Schedule { SCHED_CHAIN = 0, SCHED_WALK = 1, SCHED_LEVELS = 2 };
 
-static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* offsets, const int32_t* nodes,
-                     const int32_t* children, const int32_t* pslots, const double* pi, int flags,
+static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* offsets_in, const int32_t* nodes_in,
+                     const int32_t* children_in, const int32_t* pslots_in, const double* pi, int flags,
                      int* snapshot_out, double* lnl_out) {
   REQUIRE(c && c->n_states > 0, "cb_set_tips must come first");
-  REQUIRE(offsets && nodes && children && pslots && pi, "null argument");
+  REQUIRE(offsets_in && nodes_in && children_in && pslots_in && pi, "null argument");
   REQUIRE(snapshot_in < 0 || snapshot_valid(c, snapshot_in), "invalid snapshot %d", snapshot_in);
   const int C = c->n_cats, N = c->n_taxa, n_nodes = 2 * N;  // ids 1 .. 2N-1
+  REQUIRE(offsets_in[n_lists] > 0, "empty op list");
+
+  // ---- cherry folding (2-state family) ---------------------------------------------------------
+  // An op whose two children are tips is not run: its parent (which is always in the list) takes it
+  // as a SRC_CHERRY child and looks the cherry's 3 x 3 possible partials up.  The compacted op list
+  // replaces the caller's; fold_child remembers, per (compacted op, child), the caller's op index
+  // of the folded cherry.
+  std::vector<int32_t> offsets_v(offsets_in, offsets_in + n_lists + 1), nodes_v, children_v, pslots_v, fold_child;
+  const bool fold = c->family_s2 && !(flags & CB_EVAL_NO_FOLD);
+  if (fold) {
+    std::vector<int32_t> parent_op(n_nodes);
+    for (int li = 0; li < n_lists; ++li) {
+      const int b = offsets_in[li], e = offsets_in[li + 1];
+      std::fill(parent_op.begin(), parent_op.end(), -1);
+      for (int i = b; i < e; ++i)
+        for (int kx = 0; kx < 2; ++kx) {
+          const int ch = children_in[2 * i + kx];
+          if (ch > N && ch < n_nodes) parent_op[ch] = i;
+        }
+      offsets_v[li] = (int32_t)nodes_v.size();
+      std::vector<int32_t> folded_at(n_nodes, -1);  // node -> caller's op index of its folded cherry op
+      for (int i = b; i < e; ++i) {
+        const int node = nodes_in[i], c0 = children_in[2 * i], c1 = children_in[2 * i + 1];
+        const bool cherry = c0 >= 1 && c0 <= N && c1 >= 1 && c1 <= N && i != e - 1 && node > N && node < n_nodes &&
+                            parent_op[node] > i;
+        if (cherry) {
+          folded_at[node] = i;
+          continue;
+        }
+        nodes_v.push_back(node);
+        for (int kx = 0; kx < 2; ++kx) {
+          const int ch = children_in[2 * i + kx];
+          children_v.push_back(ch);
+          fold_child.push_back((ch > N && ch < n_nodes) ? folded_at[ch] : -1);
+          for (int q = 0; q < C; ++q) pslots_v.push_back(pslots_in[(size_t)(2 * i + kx) * C + q]);
+        }
+      }
+    }
+    offsets_v[n_lists] = (int32_t)nodes_v.size();
+  }
+  const int32_t* offsets = fold ? offsets_v.data() : offsets_in;
+  const int32_t* nodes = fold ? nodes_v.data() : nodes_in;
+  const int32_t* children = fold ? children_v.data() : children_in;
+  const int32_t* pslots = fold ? pslots_v.data() : pslots_in;
   const int total_ops = offsets[n_lists];
   REQUIRE(total_ops > 0, "empty op list");
+  std::vector<int> new_cherry_nodes, new_cherry_recs;  // folded cherries that stay in the returned snapshot
   const bool want_snap = (flags & CB_EVAL_WANT_SNAPSHOT) != 0;
   const bool store_root = (flags & CB_EVAL_STORE_ROOT) != 0;
   REQUIRE(!(want_snap && n_lists != 1), "snapshots are only kept for single evaluations");
@@ -870,9 +1004,42 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
         const int ch = children[2 * i + kx];
         op.src[kx] = nullptr;
         op.src_scale[kx] = nullptr;
+        op.ctip[kx][0] = op.ctip[kx][1] = nullptr;
+        op.crec_out[kx] = -1;
+        for (int t = 0; t < 2; ++t)
+          for (int q = 0; q < CB_S2_MAX_CATS; ++q) op.cslot[kx][t][q] = 0;
+        const int folded = fold ? fold_child[(size_t)2 * i + kx] : -1;
+        const int snap_rec = (fold && folded < 0 && ch > N && kid_op[kx][i0] < 0 && sin &&
+                              ch < (int)sin->cherry_of_node.size()) ? sin->cherry_of_node[ch] : -1;
         if (ch <= N) {
           op.kind[kx] = SRC_TIP;
           op.src[kx] = (const char*)c->d_codes + (size_t)(ch - 1) * c->P * c->code_bytes;
+        } else if (folded >= 0) {
+          // the cherry was in the caller's list: its P matrices are the caller's slots
+          op.kind[kx] = SRC_CHERRY;
+          for (int t = 0; t < 2; ++t) {
+            const int tip = children_in[2 * folded + t];
+            op.ctip[kx][t] = (const char*)c->d_codes + (size_t)(tip - 1) * c->P * c->code_bytes;
+            for (int q = 0; q < C; ++q) {
+              const int sl = pslots_in[(size_t)(2 * folded + t) * C + q];
+              REQUIRE(sl >= 0 && sl < c->pmat_cap, "op %d: P slot %d out of range", folded, sl);
+              op.cslot[kx][t][q] = sl;
+            }
+          }
+          if (want_snap) {
+            int r;
+            if (rec_acquire(c, children_in[2 * folded], children_in[2 * folded + 1], &r)) return 1;
+            op.crec_out[kx] = r;
+            new_cherry_nodes.push_back(ch);
+            new_cherry_recs.push_back(r);
+          }
+        } else if (snap_rec >= 0) {
+          // a cherry kept by the input snapshot: its P matrices live in the library's pool
+          op.kind[kx] = SRC_CHERRY;
+          for (int t = 0; t < 2; ++t) {
+            op.ctip[kx][t] = (const char*)c->d_codes + (size_t)(c->recs[snap_rec].tip[t] - 1) * c->P * c->code_bytes;
+            for (int q = 0; q < C; ++q) op.cslot[kx][t][q] = CB_LIB_SLOT | (snap_rec * 2 * C + t * C + q);
+          }
         } else if (kid_op[kx][i0] >= 0) {
           const int pp = pos_of[kid_op[kx][i0]];
           if (sched != SCHED_LEVELS && pp == p - 1 && range_id[pp] == range_id[p]) {
@@ -957,6 +1124,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     launch_maxops.push_back(mx);
   }
 
+  if (ensure_lib_pool(c)) return 1;
   // upload descriptors + pi, launch
   CU(cudaMemcpyAsync(c->d_ops, c->h_ops, (size_t)total_ops * sizeof(OpDesc), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_ranges, c->h_ranges, (size_t)n_ranges * sizeof(RangeDesc), cudaMemcpyHostToDevice, c->stream));
@@ -999,13 +1167,26 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     Snapshot& sn = c->snaps[sid];
     sin = snapshot_in >= 0 ? &c->snaps[snapshot_in] : nullptr;  // vector may have moved
     if (sin) sn.buf_of_node = sin->buf_of_node; else sn.buf_of_node.assign(n_nodes, -1);
+    if (sin) sn.cherry_of_node = sin->cherry_of_node; else sn.cherry_of_node.assign(n_nodes, -1);
     sn.buf_of_node.resize(n_nodes, -1);
+    sn.cherry_of_node.resize(n_nodes, -1);
     sn.refs = 1;
-    for (size_t i = 0; i < new_nodes.size(); ++i) sn.buf_of_node[new_nodes[i]] = -2 - (int)i;  // mark replaced
+    // a recomputed node replaces whatever the input snapshot held for it (buffer or folded cherry)
+    for (size_t i = 0; i < new_nodes.size(); ++i) {
+      sn.buf_of_node[new_nodes[i]] = -2 - (int)i;
+      sn.cherry_of_node[new_nodes[i]] = -1;
+    }
+    for (size_t i = 0; i < new_cherry_nodes.size(); ++i) {
+      sn.buf_of_node[new_cherry_nodes[i]] = -1;
+      sn.cherry_of_node[new_cherry_nodes[i]] = -2 - (int)i;
+    }
     for (int nd = 0; nd < n_nodes; ++nd) {
       int32_t& bi = sn.buf_of_node[nd];
       if (bi >= 0) c->buffers[bi].refs++;
       else if (bi <= -2) bi = new_bufs[-2 - bi];  // ownership moves from this evaluation to the snapshot
+      int32_t& ri = sn.cherry_of_node[nd];
+      if (ri >= 0) c->recs[ri].refs++;
+      else if (ri <= -2) ri = new_cherry_recs[-2 - ri];
     }
     if (snapshot_out) *snapshot_out = sid;
   } else if (snapshot_out) {

@@ -75,7 +75,7 @@ __device__ __forceinline__ void block_reduce_to_result(double v, const LaunchCon
   }
 }
 
-constexpr int S2_STAGE_OPS = 64;  // ops whose descriptors + P matrices are staged in shared memory at a time
+constexpr int S2_STAGE_OPS = 32;  // ops whose descriptors + P matrices / lookup tables are staged at a time
 
 // Vector of V doubles / ints per thread (V sites), with 8*V-byte global accesses.
 template <int V> struct VecD;
@@ -98,11 +98,6 @@ template <> __device__ __forceinline__ void load_ints<1>(const int32_t* p, int (
 template <> __device__ __forceinline__ void load_ints<2>(const int32_t* p, int (&e)[2]) {
   const int2 t = __ldcg(reinterpret_cast<const int2*>(p)); e[0] = t.x; e[1] = t.y;
 }
-template <int V> __device__ __forceinline__ void load_ints_ca(const int32_t* p, int (&e)[V]);
-template <> __device__ __forceinline__ void load_ints_ca<1>(const int32_t* p, int (&e)[1]) { e[0] = __ldca(p); }
-template <> __device__ __forceinline__ void load_ints_ca<2>(const int32_t* p, int (&e)[2]) {
-  const int2 t = __ldca(reinterpret_cast<const int2*>(p)); e[0] = t.x; e[1] = t.y;
-}
 template <int V> __device__ __forceinline__ void store_ints(int32_t* p, const int (&e)[V]);
 template <> __device__ __forceinline__ void store_ints<1>(int32_t* p, const int (&e)[1]) { __stcg(p, e[0]); }
 template <> __device__ __forceinline__ void store_ints<2>(int32_t* p, const int (&e)[2]) {
@@ -123,31 +118,57 @@ template <> __device__ __forceinline__ void load_codes<2>(const void* row, int c
   }
 }
 
-// per-op record staged in shared memory (64 B)
+// per-op record staged in shared memory (96 B)
 struct S2Stage {
   double* dst;
   int32_t* dst_scale;
   const void* src[2];
   const int32_t* src_scale[2];
+  const void* ctip[2][2];
   int32_t kind[2];
   int32_t is_root, pad_;
 };
-static_assert(sizeof(S2Stage) == 64, "S2Stage is 64 bytes");
+static_assert(sizeof(S2Stage) == 96, "S2Stage is 96 bytes");
 
-template <int V>
-__device__ __forceinline__ void fetch_codes(const S2Stage& op, int code_bytes, int64_t site, unsigned (&code)[2][V]) {
-#pragma unroll
-  for (int ch = 0; ch < 2; ++ch)
-    if (op.kind[ch] == SRC_TIP) load_codes<V>(op.src[ch], code_bytes, site, code[ch]);
-}
+// Shared-memory stage per (op, child), in doubles:
+//   internal child  [C][row] pairs (Pi0, Pi1)                                   2*2*C
+//   tip child       [C][row][4] = (Pi0, Pi1, Pi0 + Pi1, -)                      8*C
+//   cherry child    [9 code pairs][2*C + 1]: this edge's contribution v[c][i] for every pair of tip
+//                   codes of the folded cherry, and the cherry's rescale exponent            9*(2C+1)
+__host__ __device__ constexpr int s2_child_stage(int C) { return 9 * (2 * C + 1) + 1; }  // (+1: keeps 16-byte alignment)
 
 __host__ __device__ inline size_t s2_smem_bytes(int ops, int C) {
   const int n = ops < S2_STAGE_OPS ? ops : S2_STAGE_OPS;
-  return (size_t)n * (sizeof(S2Stage) + (size_t)16 * C * sizeof(double));
+  return (size_t)n * (sizeof(S2Stage) + (size_t)2 * s2_child_stage(C) * sizeof(double));
+}
+
+// codes of the tips an op reads: child ch, tip t (t = 1 only for a cherry child)
+template <int V>
+__device__ __forceinline__ void fetch_codes(const S2Stage& op, int code_bytes, int64_t site, unsigned (&code)[2][2][V]) {
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    if (op.kind[ch] == SRC_TIP) {
+      load_codes<V>(op.src[ch], code_bytes, site, code[ch][0]);
+    } else if (op.kind[ch] == SRC_CHERRY) {
+      load_codes<V>(op.ctip[ch][0], code_bytes, site, code[ch][0]);
+      load_codes<V>(op.ctip[ch][1], code_bytes, site, code[ch][1]);
+    }
+  }
+}
+
+__device__ __forceinline__ const double* s2_pmat(const LaunchConst& k, int slot) {
+  return (slot & CB_LIB_SLOT) ? k.pmats_lib + (int64_t)(slot & ~CB_LIB_SLOT) * 4 : k.pmats + (int64_t)slot * 4;
+}
+// contribution of a tip with state code `cd` through edge row (Pi0, Pi1): the FMA chain over the 0/1
+// indicator column (utils.pyx:99-111): Pi0, Pi1, or Pi0 + Pi1 for '?', '-', '0/1'
+__device__ __forceinline__ double s2_tip_term(double2 pr, int cd) {
+  return cd == 0 ? pr.x : (cd == 1 ? pr.y : fma(pr.y, 1.0, pr.x * 1.0));
 }
 
 template <int C, int V, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchConst k) {
+  static_assert(C <= CB_S2_MAX_CATS, "2-state kernel supports at most CB_S2_MAX_CATS categories");
+  constexpr int CS = s2_child_stage(C);
   extern __shared__ __align__(16) unsigned char s2_smem[];
   __shared__ double red[32];
   __shared__ int last_flag;
@@ -156,8 +177,6 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
   const int nops = rg.end - rg.begin;
   const int n_stage = min(nops, S2_STAGE_OPS);
   S2Stage* st = reinterpret_cast<S2Stage*>(s2_smem);
-  // per (op, child): 8*C doubles.  Internal child: [C][row] pairs (Pi0, Pi1) in the first half.
-  // Tip child: [C][row][4] = (Pi0, Pi1, Pi0 + Pi1, -): the edge's contribution looked up by state code.
   double* p_stage = reinterpret_cast<double*>(s2_smem + (size_t)n_stage * sizeof(S2Stage));
 
   const int64_t P = k.n_sites;
@@ -185,24 +204,75 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
       r.dst = op->dst; r.dst_scale = op->dst_scale;
       r.src[0] = op->src[0]; r.src[1] = op->src[1];
       r.src_scale[0] = op->src_scale[0]; r.src_scale[1] = op->src_scale[1];
+      r.ctip[0][0] = op->ctip[0][0]; r.ctip[0][1] = op->ctip[0][1];
+      r.ctip[1][0] = op->ctip[1][0]; r.ctip[1][1] = op->ctip[1][1];
       r.kind[0] = op->kind[0]; r.kind[1] = op->kind[1];
       r.is_root = op->is_root; r.pad_ = 0;
       st[o] = r;
     }
-    // ... their P matrices (tip children get a 3-entry lookup per row: state 0, state 1, missing) ...
+    // ... the P matrices of internal and tip children (one thread per category and row) ...
     for (int idx = threadIdx.x; idx < (o1 - o0) * 4 * C; idx += THREADS) {
       const int i = idx & 1, c = (idx >> 1) % C, ch = (idx / (2 * C)) & 1, o = idx / (4 * C);
       const OpDesc* __restrict__ op = k.ops + rg.begin + o0 + o;
-      const double2 pr = __ldg(reinterpret_cast<const double2*>(k.pmats + (int64_t)op->pslot[ch][c] * 4) + i);
-      double* base = p_stage + (size_t)(o * 2 + ch) * 8 * C;
-      if (op->kind[ch] == SRC_TIP) {
+      const int kind = op->kind[ch];
+      if (kind == SRC_CHERRY) continue;
+      const double2 pr = __ldg(reinterpret_cast<const double2*>(s2_pmat(k, op->pslot[ch][c])) + i);
+      double* base = p_stage + (size_t)(o * 2 + ch) * CS;
+      if (kind == SRC_TIP) {
         double* t = base + (c * 2 + i) * 4;
         t[0] = pr.x;
         t[1] = pr.y;
-        t[2] = fma(pr.y, 1.0, pr.x * 1.0);  // all-ones column: P[i][0] + P[i][1], as the FMA chain gives it
+        t[2] = s2_tip_term(pr, 2);
         t[3] = 0.0;
       } else {
         reinterpret_cast<double2*>(base)[c * 2 + i] = pr;
+      }
+    }
+    // ... and the lookup tables of folded cherries (one thread per pair of tip codes): exactly the
+    // arithmetic the cherry's own op and the parent's carried-child step would do per site
+    for (int idx = threadIdx.x; idx < (o1 - o0) * 2 * 9; idx += THREADS) {
+      const int q = idx % 9, ch = (idx / 9) & 1, o = idx / 18;
+      const OpDesc* __restrict__ op = k.ops + rg.begin + o0 + o;
+      if (op->kind[ch] != SRC_CHERRY) continue;
+      const int ca = q / 3, cb = q - 3 * ca;
+      double L[C][2];
+      int mh = 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const double2* pa = reinterpret_cast<const double2*>(s2_pmat(k, op->cslot[ch][0][c]));
+        const double2* pb = reinterpret_cast<const double2*>(s2_pmat(k, op->cslot[ch][1][c]));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          L[c][j] = s2_tip_term(__ldg(pa + j), ca) * s2_tip_term(__ldg(pb + j), cb);
+          mh = max(mh, __double2hiint(L[c][j]));
+        }
+      }
+      const int be = (mh >> 20) & 0x7ff;
+      const int x = (be == 0 || be == 0x7ff) ? 0 : be - 1023;
+      const double f = pow2_neg(x);
+      double* tab = p_stage + (size_t)(o * 2 + ch) * CS + q * (2 * C + 1);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const double l0 = L[c][0] * f, l1 = L[c][1] * f;
+        const double2* pp = reinterpret_cast<const double2*>(s2_pmat(k, op->pslot[ch][c]));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double2 pr = __ldg(pp + i);
+          tab[c * 2 + i] = fma(pr.y, l1, pr.x * l0);
+        }
+      }
+      tab[2 * C] = (double)x;
+      // a cherry that stays in the returned cache keeps its own copy of its two edges' P matrices
+      if (q == 0 && blockIdx.x == 0 && op->crec_out[ch] >= 0) {
+        double* out = k.pmats_lib + (int64_t)op->crec_out[ch] * 2 * C * 4;
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const double* src = s2_pmat(k, op->cslot[ch][t][c]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) out[(t * C + c) * 4 + e] = __ldg(src + e);
+          }
       }
     }
     // ... and pull this tile's tip codes of the NEXT chunk towards L2 while this chunk computes
@@ -210,11 +280,14 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
       const int nxt = min(nops, o1 + S2_STAGE_OPS) - o1;
       const int tile_bytes = THREADS * V * k.code_bytes;
       const int lines = (tile_bytes + 127) / 128;
-      for (int idx = threadIdx.x; idx < nxt * 2 * lines; idx += THREADS) {
-        const int ln = idx % lines, oc = idx / lines;
-        const OpDesc* __restrict__ op = k.ops + rg.begin + o1 + (oc >> 1);
-        if (op->kind[oc & 1] == SRC_TIP) {
-          const char* a = static_cast<const char*>(op->src[oc & 1]) + tile0 * k.code_bytes + ln * 128;
+      for (int idx = threadIdx.x; idx < nxt * 4 * lines; idx += THREADS) {
+        const int ln = idx % lines, oc = idx / lines;  // oc: op (2 bits below: child, tip)
+        const OpDesc* __restrict__ op = k.ops + rg.begin + o1 + (oc >> 2);
+        const int ch = (oc >> 1) & 1, t = oc & 1;
+        const int kind = op->kind[ch];
+        const void* row = kind == SRC_TIP ? (t == 0 ? op->src[ch] : nullptr) : (kind == SRC_CHERRY ? op->ctip[ch][t] : nullptr);
+        if (row != nullptr) {
+          const char* a = static_cast<const char*>(row) + tile0 * k.code_bytes + ln * 128;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         }
       }
@@ -223,16 +296,18 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
     if (!active) continue;
     // tip codes are fetched one op ahead (register prefetch): by the time an op starts, its codes
     // have had a whole op of compute to arrive from L2
-    unsigned code_next[2][V];
+    unsigned code_next[2][2][V];
     fetch_codes<V>(st[0], k.code_bytes, site, code_next);
 #pragma unroll 1
     for (int o = o0; o < o1; ++o) {
       const S2Stage& op = st[o - o0];
-      unsigned code[2][V];
+      unsigned code[2][2][V];
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-        for (int v = 0; v < V; ++v) code[ch][v] = code_next[ch][v];
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int v = 0; v < V; ++v) code[ch][t][v] = code_next[ch][t][v];
       if (o + 1 < o1) fetch_codes<V>(st[o + 1 - o0], k.code_bytes, site, code_next);
 
       VecD<V> out[C][2];
@@ -242,7 +317,7 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         const int kind = op.kind[ch];
-        const double* pbase = p_stage + (size_t)((o - o0) * 2 + ch) * 8 * C;
+        const double* pbase = p_stage + (size_t)((o - o0) * 2 + ch) * CS;
         const double2* pm = reinterpret_cast<const double2*>(pbase);  // (P[i][0], P[i][1]) broadcasts
         // v[i] = P[i][0] L[0] + P[i][1] L[1]; first child initialises `out`, second multiplies into it
 #define CB_S2_APPLY(L0, L1)                                                   \
@@ -272,7 +347,8 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
           CB_S2_APPLY(L[c][0].v[v], L[c][1].v[v])
 #pragma unroll
           for (int v = 0; v < V; ++v) e_in[v] += se[v];
-        } else {  // tip: state code 0 / 1 / 2 ('?', '-', '0/1') selects the staged contribution of this edge
+        } else if (kind == SRC_TIP) {
+          // state code 0 / 1 / 2 ('?', '-', '0/1') selects the staged contribution of this edge
           // (= the FMA chain over the 0/1 indicator column of utils.pyx:99-111, bit for bit)
 #pragma unroll
           for (int c = 0; c < C; ++c) {
@@ -280,10 +356,24 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
             for (int i = 0; i < 2; ++i) {
 #pragma unroll
               for (int v = 0; v < V; ++v) {
-                const double x = pbase[(c * 2 + i) * 4 + min(code[ch][v], 2u)];
+                const double x = pbase[(c * 2 + i) * 4 + min(code[ch][0][v], 2u)];
                 if (ch == 0) out[c][i].v[v] = x; else out[c][i].v[v] *= x;
               }
             }
+          }
+        } else {  // folded cherry: the pair of tip codes selects a precomputed row
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const double* tab = pbase + (min(code[ch][0][v], 2u) * 3 + min(code[ch][1][v], 2u)) * (2 * C + 1);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const double x = tab[c * 2 + i];
+                if (ch == 0) out[c][i].v[v] = x; else out[c][i].v[v] *= x;
+              }
+            }
+            e_in[v] += (int)tab[2 * C];
           }
         }
 #undef CB_S2_APPLY

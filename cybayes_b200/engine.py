@@ -12,7 +12,7 @@ import weakref
 import numpy as np
 
 from . import _lib
-from ._lib import (CB_EVAL_FORCE_LEVELS, CB_EVAL_FORCE_WALK, CB_EVAL_NO_SYNC, CB_EVAL_STORE_ROOT, CB_EVAL_WANT_SNAPSHOT, c_f64p,
+from ._lib import (CB_EVAL_FORCE_LEVELS, CB_EVAL_FORCE_WALK, CB_EVAL_NO_FOLD, CB_EVAL_NO_SYNC, CB_EVAL_STORE_ROOT, CB_EVAL_WANT_SNAPSHOT, c_f64p,
                    c_i32p, check)
 
 
@@ -167,12 +167,12 @@ class Engine(SlotPool):
 
     # ------------------------------------------------------------------ evaluation
     def eval(self, snapshot, nodes, children, pslots, pi, want_snapshot=True, store_root=False,
-             force_levels=False, sync=True, force_walk=False):
+             force_levels=False, sync=True, force_walk=False, no_fold=False):
         """Run the op list (see cb_eval).  Returns (lnL, snapshot id or -1)."""
         self.flush_builds()
         flags = (CB_EVAL_WANT_SNAPSHOT if want_snapshot else 0) | (CB_EVAL_STORE_ROOT if store_root else 0) \
             | (CB_EVAL_FORCE_LEVELS if force_levels else 0) | (0 if sync else CB_EVAL_NO_SYNC) \
-            | (CB_EVAL_FORCE_WALK if force_walk else 0)
+            | (CB_EVAL_FORCE_WALK if force_walk else 0) | (CB_EVAL_NO_FOLD if no_fold else 0)
         pi = np.ascontiguousarray(pi, dtype=np.float64)
         check(self._lib.cb_eval(self._ctx, -1 if snapshot is None else int(snapshot), nodes.size, _i32(nodes),
                                 _i32(children), _i32(pslots), _f64(pi), flags, C.byref(self._snap),

@@ -55,7 +55,8 @@ enum {
                              /* root kernel does not need it)                                   */
   CB_EVAL_NO_SYNC = 4,       /* enqueue only; the result is read later with cb_result_wait      */
   CB_EVAL_FORCE_LEVELS = 8,  /* never use the single-launch path walk, even for a chain         */
-  CB_EVAL_FORCE_WALK = 16    /* single-launch depth-first walk even on a small alignment (tests)  */
+  CB_EVAL_FORCE_WALK = 16,   /* single-launch depth-first walk even on a small alignment (tests)  */
+  CB_EVAL_NO_FOLD = 32       /* 2-state family: run cherries as ordinary ops instead of folding them */
 };
 
 const char* cb_last_error(void);

@@ -89,7 +89,7 @@ class FakeEngine(SlotPool):
         return lnl, base, new
 
     def eval(self, snapshot, nodes, children, pslots, pi, want_snapshot=True, store_root=False,
-             force_levels=False, sync=True, force_walk=False):
+             force_levels=False, sync=True, force_walk=False, no_fold=False):
         self.n_evals += 1
         lnl, base, new = self._run(snapshot, nodes, children, pslots, np.asarray(pi, dtype=float))
         sid = -1

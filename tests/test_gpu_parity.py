@@ -179,6 +179,12 @@ def test_random_inputs_vs_oracle(S, n_taxa, n_sites, model, gpu_backend):
     l_walk2, _ = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=False, force_walk=True)
     l_lev, _ = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=False, force_levels=True)
     assert l_walk == lnl and l_walk2 == lnl and l_lev == lnl
+    # 2-state family: cherries folded into their parents (default) vs run as ordinary ops: same bits
+    l_nf, s_nf = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=True, no_fold=True)
+    assert l_nf == lnl
+    for node in plan.nodes.tolist()[:-1]:
+        assert np.array_equal(eng.read_partial(s_nf, node), eng.read_partial(snap, node))
+    eng.release_snapshot(s_nf)
     # small shards cut the walk into parallel subtrees + a top part (two launches): same bits
     os.environ["CYBAYES_WALK_SPLIT"] = "3"
     try:
