@@ -199,6 +199,10 @@ def test_random_inputs_vs_oracle(S, n_taxa, n_sites, model, gpu_backend):
     for node in plan.nodes.tolist()[:-1]:
         assert np.array_equal(eng.read_partial(s_walk, node), eng.read_partial(snap, node))
     eng.release_snapshot(s_walk)
+    # asynchronous form: enqueue now (CB_EVAL_NO_SYNC), collect the number later (cb_result_wait)
+    _, s_async = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=True, sync=False)
+    assert eng.wait() == lnl
+    eng.release_snapshot(s_async)
     # (b) device-built matrices
     block2 = eng.alloc_slots(n_e * C)
     slots2 = np.arange(block2.base, block2.base + n_e * C, dtype=np.int32)
