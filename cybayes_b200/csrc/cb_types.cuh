@@ -43,6 +43,7 @@ struct LaunchConst {
   const RangeDesc* ranges;
   const double* pmats;     // slot pool, S*S doubles per slot
   double* pmats_lib;       // library-owned slots (copies of the P matrices of folded cherries)
+  const double* staged;    // register-carried DMMA kernel: P matrices re-laid out in consumption order (rc_restage_kernel)
   const double* weights;   // [P]
   const double* pi;        // [S]
   const double* amb;       // [n_amb][S] 0/1
@@ -54,6 +55,8 @@ struct LaunchConst {
   int64_t n_sites;         // padded pattern count P (multiple of 64)
   int32_t n_states, n_cats, code_bytes, max_blocks;
   double cats;            // n_cats as a double (the reference divides, ML_gamma.pyx:38)
+  int32_t rc_stagger;     // register-carried DMMA kernel: start offset between the warps of a sub-partition (cycles)
+  int32_t pad_;
 };
 
 }  // namespace cb

@@ -22,6 +22,7 @@
 
 #include "cb_types.cuh"
 #include "kernels_dmma.cuh"
+#include "kernels_dmma_rc.cuh"
 #include "kernels_general.cuh"
 #include "kernels_pmat.cuh"
 #include "kernels_s2.cuh"
@@ -96,6 +97,8 @@ static int load_nccl() {
 enum { NCCL_DOUBLE = 8, NCCL_SUM = 0 };  // ncclFloat64 / ncclSum in nccl.h
 
 // ------------------------------------------------------------------------------ context
+constexpr int64_t DMMA_RC_MIN_SITES = 16384;  // below this 128-site blocks x C cannot fill 148 SMs
+
 struct Buffer {
   double* data = nullptr;
   int32_t* scale = nullptr;
@@ -123,6 +126,10 @@ struct cb_ctx {
   int64_t n_sites = 0, P = 0;  // real and padded pattern counts
   bool family_s2 = false;
   bool use_dmma = false;  // general family, 32 <= S <= 64: FP64 tensor-core kernel (below that the plain kernel wins)
+  bool dmma_rc = false;   // ... its register-carried variant (128-site blocks): large alignments, compile-time S
+  int rc_stagger = 1;     // anti-lockstep barriers between the warps of one SM sub-partition, see kernels_dmma_rc.cuh
+  double* d_staged = nullptr;  // P matrices of the current evaluation in stage layout and consumption order
+  size_t staged_bytes = 0;
   int s2_vec = 1;  // sites per thread of the 2-state kernel on large alignments
   int s2_minb = 3; // its __launch_bounds__ min blocks per SM (experiment knob)
   void* d_codes = nullptr;
@@ -223,6 +230,10 @@ static int create_impl(int device, cb_ctx** out) {
 #define CB_DMMA_ATTR(SS) CU(cudaFuncSetAttribute(prune_dmma_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
   CB_DMMA_ATTR(0); CB_DMMA_ATTR(32); CB_DMMA_ATTR(40); CB_DMMA_ATTR(47); CB_DMMA_ATTR(48); CB_DMMA_ATTR(56); CB_DMMA_ATTR(64);
 #undef CB_DMMA_ATTR
+#define CB_RC_ATTR(SS) CU(cudaFuncSetAttribute(prune_dmma_rc_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RcCfg<SS>::SMEM))
+  CB_RC_ATTR(32); CB_RC_ATTR(40); CB_RC_ATTR(47); CB_RC_ATTR(48); CB_RC_ATTR(56); CB_RC_ATTR(64);
+#undef CB_RC_ATTR
+  if (const char* v = getenv("CYBAYES_RC_STAGGER")) c->rc_stagger = atoi(v) != 0;
   *out = c;
   return 0;
 }
@@ -243,6 +254,9 @@ static void free_alignment(cb_ctx* c) {
   if (c->d_amb) dev_free(c, c->d_amb, (size_t)std::max(1, c->n_amb) * c->n_states * 8);
   if (c->d_pi) dev_free(c, c->d_pi, (size_t)c->n_states * 8);
   if (c->d_pmats) dev_free(c, c->d_pmats, (size_t)c->pmat_cap * c->n_states * c->n_states * 8);
+  if (c->d_staged) dev_free(c, c->d_staged, c->staged_bytes);
+  c->d_staged = nullptr;
+  c->staged_bytes = 0;
   c->d_codes = nullptr;
   c->d_weights = c->d_amb = c->d_pi = c->d_pmats = nullptr;
   c->pmat_cap = 0;
@@ -349,6 +363,13 @@ static int set_tips_impl(cb_ctx* c, int n_taxa, int64_t n_sites, int n_states, i
   c->P = (n_sites + 63) / 64 * 64;
   c->family_s2 = (n_states == 2 && (n_cats == 4 || n_cats == 1));
   c->use_dmma = !c->family_s2 && n_states >= 32 && n_states <= 64 && !getenv("CYBAYES_NO_DMMA");
+  {
+    // The kernel is fixed per alignment (never per schedule), so every evaluation of an alignment sums in one order.
+    // The register-carried variant needs 128-site blocks x C to fill the GPU: large alignments only (CYBAYES_DMMA_RC=1/0 forces).
+    const bool ct = n_states == 32 || n_states == 40 || n_states == 47 || n_states == 48 || n_states == 56 || n_states == 64;
+    const char* v = getenv("CYBAYES_DMMA_RC");
+    c->dmma_rc = c->use_dmma && ct && (v ? atoi(v) != 0 : c->P >= DMMA_RC_MIN_SITES);
+  }
   const int64_t P = c->P;
   if (dev_alloc(c, &c->d_codes, (size_t)n_taxa * P * code_bytes)) return 1;
   // padding sites carry the all-ones code (a no-op factor) and weight 0
@@ -660,6 +681,7 @@ static LaunchConst make_const(cb_ctx* c) {
   k.ranges = c->d_ranges;
   k.pmats = c->d_pmats;
   k.pmats_lib = c->d_pmats_lib;
+  k.staged = c->d_staged;
   k.weights = c->d_weights;
   k.pi = c->d_pi;
   k.amb = c->d_amb;
@@ -674,6 +696,8 @@ static LaunchConst make_const(cb_ctx* c) {
   k.code_bytes = c->code_bytes;
   k.max_blocks = c->max_blocks;
   k.cats = (double)c->n_cats;
+  k.rc_stagger = c->rc_stagger;
+  k.pad_ = 0;
   return k;
 }
 
@@ -716,6 +740,14 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
       if (small) CB_LAUNCH_S2(1, 1, 64, 8); else if (V == 1) CB_LAUNCH_S2(1, 1, 256, 4); else CB_LAUNCH_S2(1, 2, 256, 4);
     }
 #undef CB_LAUNCH_S2
+  } else if (c->dmma_rc) {
+    dim3 grid((unsigned)((c->P + RC_T - 1) / RC_T), (unsigned)n_r, (unsigned)c->n_cats);
+    switch (c->n_states) {
+#define CB_RC_CASE(SS) case SS: prune_dmma_rc_kernel<SS><<<grid, RC_THREADS, RcCfg<SS>::SMEM, c->stream>>>(kk); break
+      CB_RC_CASE(32); CB_RC_CASE(40); CB_RC_CASE(47); CB_RC_CASE(48); CB_RC_CASE(56); CB_RC_CASE(64);
+#undef CB_RC_CASE
+      default: return fail("internal error: no register-carried DMMA kernel for %d states", c->n_states);
+    }
   } else if (c->use_dmma) {
     dim3 grid((unsigned)(c->P / DM_T), (unsigned)n_r, (unsigned)c->n_cats);
     const size_t smem = dm_smem_bytes(c->n_states);
@@ -901,9 +933,9 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
       // the ops above the cut follow in a second launch.
       int limit = n + 1;
       {
-        const int64_t tile_sites = c->family_s2 ? (int64_t)256 * c->s2_vec : (c->use_dmma ? DM_T : GEN_T);
+        const int64_t tile_sites = c->family_s2 ? (int64_t)256 * c->s2_vec : (c->dmma_rc ? RC_T : (c->use_dmma ? DM_T : GEN_T));
         const int64_t blocks = (c->P + tile_sites - 1) / tile_sites * (c->family_s2 ? 1 : c->n_cats);
-        const int64_t slots = (int64_t)c->sm_count * (c->family_s2 ? (c->s2_vec == 1 ? 3 : 2) : 2);
+        const int64_t slots = (int64_t)c->sm_count * (c->family_s2 ? (c->s2_vec == 1 ? 3 : 2) : (c->dmma_rc ? 1 : 2));
         if (blocks < 4 * slots && n >= 64 && !(flags & CB_EVAL_FORCE_WALK))
           limit = std::max(16, std::min(256, (int)(n * blocks / (8 * slots)) + 1));
         if (getenv("CYBAYES_WALK_SPLIT")) limit = std::max(2, atoi(getenv("CYBAYES_WALK_SPLIT")));
@@ -1132,8 +1164,33 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   CU(cudaEventRecord(c->ev_stage, c->stream));
   c->h2d += (int64_t)total_ops * sizeof(OpDesc) + (int64_t)n_ranges * sizeof(RangeDesc) + c->n_states * 8;
 
+  if (c->dmma_rc) {
+    // every P matrix the ops use, re-laid out into the shared-memory stage image, in consumption order
+    const int S8 = (c->n_states + 7) / 8 * 8;
+    const size_t need = (size_t)total_ops * 2 * C * S8 * S8 * 8;
+    if (need > c->staged_bytes) {
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->d_staged) dev_free(c, c->d_staged, c->staged_bytes);
+      c->d_staged = nullptr;
+      c->staged_bytes = 0;
+      const size_t cap = std::max(need, (size_t)64 << 20);
+      if (dev_alloc(c, (void**)&c->d_staged, cap)) return 1;
+      c->staged_bytes = cap;
+    }
+  }
   const LaunchConst k = make_const(c);
   CU(cudaEventRecord(c->ev0, c->stream));
+  if (c->dmma_rc) {
+    const unsigned jobs = (unsigned)(total_ops * 2 * C);
+    switch (c->n_states) {
+#define CB_RS_CASE(SS) case SS: rc_restage_kernel<SS><<<jobs, 256, 0, c->stream>>>(k, total_ops, c->d_staged); break
+      CB_RS_CASE(32); CB_RS_CASE(40); CB_RS_CASE(47); CB_RS_CASE(48); CB_RS_CASE(56); CB_RS_CASE(64);
+#undef CB_RS_CASE
+      default: return fail("internal error: no register-carried DMMA kernel for %d states", c->n_states);
+    }
+    CU(cudaGetLastError());
+    c->launches += 1;
+  }
   for (size_t li = 0; li < launches.size(); ++li)
     if (launch_ranges(c, k, launches[li].first, launches[li].second, launch_maxops[li])) return 1;
   if (!c->family_s2) {

@@ -142,6 +142,21 @@ def _oracle_leaves(codes, S, amb):
 def test_random_inputs_vs_oracle(S, n_taxa, n_sites, model, gpu_backend):
     """Engine called directly with host P matrices (cb_pmat_upload) and with device-built ones
     (cb_pmat_build): lnL, every cached partial and the batched P builder against the oracle."""
+    _check_random_inputs(S, n_taxa, n_sites, model)
+
+
+@pytest.mark.parametrize("S,n_taxa,n_sites,model", [(64, 8, 100, "GTR"), (47, 10, 64, "GTR"), (40, 7, 90, "GTR"),
+                                                    (32, 9, 300, "F81"), (56, 12, 200, "JC"), (48, 6, 129, "GTR"),
+                                                    (64, 33, 1000, "F81")])
+def test_random_inputs_register_carried_dmma(S, n_taxa, n_sites, model, gpu_backend, monkeypatch):
+    """The same checks with the large-alignment FP64 tensor kernel (kernels_dmma_rc.cuh: partial carried in
+    mma fragments, P matrices streamed by a producer warp) forced onto small inputs: ragged last blocks
+    (64 of 128 sites), padded state counts (47), missing cells and ambiguity sets in every tile."""
+    monkeypatch.setenv("CYBAYES_DMMA_RC", "1")
+    _check_random_inputs(S, n_taxa, n_sites, model)
+
+
+def _check_random_inputs(S, n_taxa, n_sites, model):
     from cybayes_b200 import _lib
     from cybayes_b200.engine import Engine
     from cybayes_b200.likelihood import _Plan
