@@ -218,16 +218,31 @@ __device__ __forceinline__ void rc_contract(double (&acc)[2][RcCfg<S>::NT][2], c
   const int hb = (swg >> 3) & 1;
   const double* p_even = Pm + g * PS + ((2 * t4) ^ (swg & 7)) + 8 * hb;
   const double* p_odd = p_even - 16 * hb;
+  // Issue order: per k pair j, groups of up to four state tiles -- first all their (j,0) blocks, then all their (j,1)
+  // blocks -- so a DMMA never depends on one of the 7 issued before it (a lone warp would otherwise wait on the
+  // ~27-cycle accumulate latency every other instruction).
+  constexpr int NG = 4;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     const double* pj = ((j & 1) ? p_odd : p_even) + 8 * j;
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const double2 b = *reinterpret_cast<const double2*>(pj + (8 * n) * PS);
-      rc_dmma(acc[0][n][0], acc[0][n][1], cur[0][j][0], b.x);
-      rc_dmma(acc[1][n][0], acc[1][n][1], cur[1][j][0], b.x);
-      rc_dmma(acc[0][n][0], acc[0][n][1], cur[0][j][1], b.y);
-      rc_dmma(acc[1][n][0], acc[1][n][1], cur[1][j][1], b.y);
+    for (int n0 = 0; n0 < NT; n0 += NG) {
+      double2 b[NG];
+#pragma unroll
+      for (int i = 0; i < NG; ++i)
+        if (n0 + i < NT) b[i] = *reinterpret_cast<const double2*>(pj + (8 * (n0 + i)) * PS);
+#pragma unroll
+      for (int i = 0; i < NG; ++i)
+        if (n0 + i < NT) {
+          rc_dmma(acc[0][n0 + i][0], acc[0][n0 + i][1], cur[0][j][0], b[i].x);
+          rc_dmma(acc[1][n0 + i][0], acc[1][n0 + i][1], cur[1][j][0], b[i].x);
+        }
+#pragma unroll
+      for (int i = 0; i < NG; ++i)
+        if (n0 + i < NT) {
+          rc_dmma(acc[0][n0 + i][0], acc[0][n0 + i][1], cur[0][j][1], b[i].y);
+          rc_dmma(acc[1][n0 + i][0], acc[1][n0 + i][1], cur[1][j][1], b[i].y);
+        }
     }
   }
 }
