@@ -152,17 +152,33 @@ def run_real(name):
 
 
 def run_c5(n_patterns, n_taxa=512, S=64):
+    """C5, on one GPU or -- under `python -m torch.distributed.run --nproc-per-node N bench_configs.py C5 ...` -- with the
+    patterns sharded over N GPUs (one process each; the library all-reduces the scalar lnL over NCCL).  The full-size
+    cache (209 GB) needs >= 2 GPUs."""
     from cybayes_b200 import _lib
     from cybayes_b200.engine import Engine
     from cybayes_b200.likelihood import _Plan
     from cybayes_b200.subst import gtr_eigensystem
-    from cybayes_b200.synthetic import SyntheticAlignment
-    aln = SyntheticAlignment(n_taxa, n_patterns, S, 20260102, block_sites=min(n_patterns, 25000))
+    from cybayes_b200.synthetic import SyntheticAlignment, shard_bounds
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # host-side rendezvous only (gloo)
+        dist.init_process_group("gloo")
+        os.environ["CYBAYES_DEVICE"] = os.environ.get("LOCAL_RANK", "0")
+    block_sites = min(n_patterns, 25000)
+    aln = SyntheticAlignment(n_taxa, n_patterns, S, 20260102, block_sites=block_sites)
+    lo, hi = shard_bounds(n_patterns, rank, world, block_sites) if world > 1 else (0, n_patterns)
     t0 = time.perf_counter()
-    codes = aln.codes(0, n_patterns)
+    codes = aln.codes(lo, hi)
     t_gen = time.perf_counter() - t0
+    n_local = hi - lo
     C = 4
     eng = Engine(codes, S, C)
+    if world > 1:
+        box = [eng.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(box[0], rank, world)
     plan = _Plan(aln.edge_order())
     ekeys = list(aln.tree.keys())
     n_e = len(ekeys)
@@ -181,22 +197,36 @@ def run_c5(n_patterns, n_taxa=512, S=64):
     alg_bytes = 16.0 * C * S * n_patterns * (n_taxa - 2) + 1.0 * n_taxa * n_patterns + 8.0 * n_patterns
     res = {}
     for label, snap in (("lnl_only", False), ("with_cache", True)):
-        need = (n_taxa - 2) * C * S * n_patterns * 8 if snap else 0
+        need = (n_taxa - 2) * C * S * n_local * 8 if snap else 0
         if need > 150e9:
-            res[label] = {"skipped": f"cache of {need / 1e9:.0f} GB does not fit one GPU"}
+            res[label] = {"skipped": f"cache of {need / 1e9:.0f} GB per GPU does not fit"}
             continue
         ms = []
         for _ in range(4):
+            if dist is not None:
+                dist.barrier()
+            eng.mark(0)
             lnl, sn = eng.eval(None, plan.nodes, plan.children, pslots, aln.pi, want_snapshot=snap)
-            ms.append(eng.last_eval_ms())
+            eng.mark(1)
+            ms.append(eng.mark_elapsed_ms() if world > 1 else eng.last_eval_ms())   # sharded: incl. the all-reduce
             if sn >= 0:
                 eng.release_snapshot(sn)
         m = statistics.median(ms[1:])
+        if dist is not None:
+            import torch
+            t = torch.tensor([m], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)   # slowest rank
+            m = float(t[0])
         res[label] = {"ms": m, "evals_per_sec": 1e3 / m, "tflops": flops / m / 1e9, "alg_GBps": alg_bytes / m / 1e6,
                       "lnL": lnl}
-    print(json.dumps({"config": "C5", "n_taxa": n_taxa, "n_patterns": n_patterns, "n_states": S, "model": "GTR",
-                      "algorithmic_tflop": flops / 1e12, "algorithmic_GB": alg_bytes / 1e9, "k1_pmat_build_ms": k1_ms,
-                      "n_matrices": n_e * C, "data_generation_s": t_gen, **res}), flush=True)
+    if rank == 0:
+        print(json.dumps({"config": "C5", "n_gpus": world, "n_taxa": n_taxa, "n_patterns": n_patterns, "n_states": S,
+                          "model": "GTR", "patterns_per_gpu": n_local, "algorithmic_tflop": flops / 1e12,
+                          "algorithmic_GB": alg_bytes / 1e9, "k1_pmat_build_ms": k1_ms, "n_matrices": n_e * C,
+                          "data_generation_s": t_gen, **res}), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
