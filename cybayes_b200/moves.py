@@ -67,10 +67,22 @@ def scale_alpha(alpha):
     return new_alpha, log_c, -(new_alpha - alpha)
 
 
+def _shuffle(x, getrandbits=random.getrandbits):
+    """random.shuffle(x), draw for draw (Fisher-Yates from the top; randbelow by rejection on bit_length bits), without
+    a Python-level call per element -- the shuffle of the edge list is a third of the cost of an NNI proposal."""
+    for i in range(len(x) - 1, 0, -1):
+        n = i + 1
+        k = n.bit_length()
+        r = getrandbits(k)
+        while r >= n:
+            r = getrandbits(k)
+        x[i], x[r] = x[r], x[i]
+
+
 def _nni(tree, root_node):
     kids = adjlist2nodes_dict(tree)
     order = list(tree.keys())
-    random.shuffle(order)
+    _shuffle(order)
     for a, b in order:
         if b > config.N_TAXA:
             break
@@ -81,7 +93,10 @@ def _nni(tree, root_node):
     del tree[a, src], tree[b, tgt]
     tree[a, tgt] = tgt_bl
     tree[b, src] = src_bl
-    new_postorder = postorder(adjlist2nodes_dict(tree), root_node)[::-1]
+    # children lists of the new tree (= adjlist2nodes_dict(tree)): the two re-inserted edges are last in the dict
+    kids[a] = [c for c in sib_a if c != src] + [tgt]
+    kids[b] = [c for c in kids_b if c != tgt] + [src]
+    new_postorder = postorder(kids, root_node)[::-1]
     nodes_recompute = [b] + get_path2root(adjlist2reverse_nodes_dict(tree), b, root_node)
     return tree, new_postorder, 0.0, nodes_recompute, [a, b, src, tgt]
 
