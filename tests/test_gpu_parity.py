@@ -138,7 +138,9 @@ def _oracle_leaves(codes, S, amb):
 @pytest.mark.parametrize("S,n_taxa,n_sites,model", [(2, 2, 70, "F81"), (5, 3, 10, "GTR"), (2, 12, 333, "F81"),
                                                     (2, 40, 1000, "GTR"), (4, 9, 65, "GTR"), (40, 7, 90, "GTR"),
                                                     (6, 17, 200, "F81"), (23, 14, 129, "JC"), (47, 10, 64, "GTR"),
-                                                    (64, 8, 100, "GTR"), (130, 6, 40, "F81")])
+                                                    (64, 8, 100, "GTR"), (130, 6, 40, "F81"),
+                                                    # >= 16384 patterns: the register-carried FP64 tensor kernel by default
+                                                    (64, 12, 16500, "GTR"), (47, 9, 16400, "F81")])
 def test_random_inputs_vs_oracle(S, n_taxa, n_sites, model, gpu_backend):
     """Engine called directly with host P matrices (cb_pmat_upload) and with device-built ones
     (cb_pmat_build): lnL, every cached partial and the batched P builder against the oracle."""
