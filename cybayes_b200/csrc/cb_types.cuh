@@ -55,8 +55,8 @@ struct LaunchConst {
   int64_t n_sites;         // padded pattern count P (multiple of 64)
   int32_t n_states, n_cats, code_bytes, max_blocks;
   double cats;            // n_cats as a double (the reference divides, ML_gamma.pyx:38)
-  int32_t rc_stagger;     // register-carried DMMA kernel: start offset between the warps of a sub-partition (cycles)
-  int32_t pad_;
+  int32_t rc_stagger;     // register-carried DMMA kernel: anti-lockstep barriers between the warps of a sub-partition
+  int32_t n_amb;          // rows of `amb`
 };
 
 }  // namespace cb

@@ -697,7 +697,7 @@ static LaunchConst make_const(cb_ctx* c) {
   k.max_blocks = c->max_blocks;
   k.cats = (double)c->n_cats;
   k.rc_stagger = c->rc_stagger;
-  k.pad_ = 0;
+  k.n_amb = c->n_amb;
   return k;
 }
 
@@ -1167,7 +1167,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   if (c->dmma_rc) {
     // every P matrix the ops use, re-laid out into the shared-memory stage image, in consumption order
     const int S8 = (c->n_states + 7) / 8 * 8;
-    const size_t need = (size_t)total_ops * 2 * C * S8 * S8 * 8;
+    const size_t need = (size_t)total_ops * 2 * C * (S8 + RC_EXTRA_ROWS) * S8 * 8;
     if (need > c->staged_bytes) {
       CU(cudaStreamSynchronize(c->stream));
       if (c->d_staged) dev_free(c, c->d_staged, c->staged_bytes);

@@ -18,13 +18,14 @@
 //     copies completing on an mbarrier -- no LSU work, no registers, no producer warp: the warp that
 //     is LAST to finish with a stage (shared-memory counter) re-arms its barrier and issues the
 //     copy of the matrix NST jobs ahead.  The op descriptor travels with the first child's matrix.
-//   * The swizzle makes the B fragments of two k blocks one conflict-free LDS.128, and lets the four
-//     lanes of a quad gathering one column of four rows (tip children) hit four different banks.
+//   * The swizzle makes the B fragments of two k blocks one conflict-free LDS.128.
+//   * For a TIP child the staged image is P TRANSPOSED, followed by precomputed rows for the non-state codes: row S
+//     holds the row sums of P ('?' / '-' cells), rows S+1.. the dot products with the other ambiguity sets.  A tip
+//     child is then one row per site, read as 16-byte pairs straight into the accumulator layout: no tensor work, no
+//     per-warp row sums, no shuffles, no branch on missing data.
 //   * Buffer children (nodes with two internal children, inputs of a dirty path) are loaded from
 //     HBM straight into A-fragment registers: per request 4 rows x 64 contiguous bytes, every
 //     sector fully used; a thread reads back exactly the addresses it wrote itself.
-//   * Tip children skip the tensor cores: one-hot = column gather of P from the stage,
-//     all-ones = row sums (computed by the warp only when a tile has such a cell).
 //   * Per site rescale (power of two, integer max of the high words) and the store of the cached
 //     partial come straight from the accumulator registers; max / pi-dot reductions are two
 //     shuffles inside a quad.
@@ -47,13 +48,15 @@ constexpr int RC_THREADS = RC_WARPS * 32;
 constexpr int RC_WSITES = 16;                     // sites per warp (two 8-row m-tiles)
 constexpr int RC_T = RC_WARPS * RC_WSITES;        // sites per block
 constexpr int RC_DESC_D = sizeof(OpDesc) / 8;     // doubles taken by the op descriptor copy of a stage
+constexpr int RC_EXTRA_ROWS = 8;                  // rows of a tip image beyond the padded states: codes S .. (row sums, ambiguity sets)
 
 template <int S> struct RcCfg {
   static constexpr int S8 = (S + 7) / 8 * 8;
   static constexpr int NT = S8 / 8;                                  // 8-state tiles (n tiles = k block pairs)
   static constexpr int PS = S8;                                      // P row stride in a stage (unpadded, swizzled)
   static constexpr bool SWZ_HALF = (S8 % 16 == 0);                   // rows start in the same 128-byte bank window
-  static constexpr int MAT_D = S8 * PS;
+  static constexpr int ROWS = S8 + RC_EXTRA_ROWS;                    // rows of a stage image
+  static constexpr int MAT_D = ROWS * PS;
   static constexpr unsigned MAT_BYTES = MAT_D * 8;
   static constexpr int STAGE_D = MAT_D + RC_DESC_D;
   static constexpr int NST_FIT = (226 * 1024) / (STAGE_D * 8);
@@ -93,6 +96,17 @@ __device__ __forceinline__ void rc_mbar_wait(void* bar, unsigned parity) {
       "RC_DONE_%=:\n"
       "}\n" ::"r"(a), "r"(parity) : "memory");
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool rc_mbar_test(void* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      " selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(rc_smem_addr(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // bulk-async copy global -> shared, completion counted in bytes on the mbarrier
 __device__ __forceinline__ void rc_bulk_g2s(void* smem, const void* gmem, unsigned bytes, void* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(rc_smem_addr(smem)),
@@ -107,11 +121,14 @@ __device__ __forceinline__ void rc_dmma(double& c0, double& c1, double a, double
 }
 
 // Pre-pass of an evaluation: staged[((o * 2 + step) * C + c)] <- pool slot ops[o].pslot[child(step)][c], as a stage image.
+//   internal child:  rows i < S8: P[i][.] with the 16-byte units of the row swizzled by rc_swz(i) (B fragments);
+//   tip child:       row r < S: P[.][r] (P transposed); row S: sum_j P[.][j]; row S + k: sum_j P[.][j] amb[k][j];
+//                    unit index ^= (r & 1) << 2 when rows are a multiple of 128 bytes (two sites' rows in different banks).
 // One block per matrix.
 template <int S>
 __global__ void __launch_bounds__(256) rc_restage_kernel(const LaunchConst k, int n_ops, double* __restrict__ staged) {
   using Cfg = RcCfg<S>;
-  constexpr int S8 = Cfg::S8, U = S8 / 2;   // 16-byte units per row
+  constexpr int S8 = Cfg::S8, U = S8 / 2, ROWS = Cfg::ROWS;   // U: 16-byte units per row
   const int job = blockIdx.x;               // (o * 2 + step) * C + c
   const int C = k.n_cats;
   const int c = job % C, os = job / C, step = os & 1, o = os >> 1;
@@ -121,14 +138,40 @@ __global__ void __launch_bounds__(256) rc_restage_kernel(const LaunchConst k, in
   const int child = step ? 1 - first : first;
   const double* __restrict__ pm = k.pmats + (int64_t)op->pslot[child][c] * S * S;
   double2* dst = reinterpret_cast<double2*>(staged + (int64_t)job * Cfg::MAT_D);
-  for (int idx = threadIdx.x; idx < S8 * U; idx += blockDim.x) {
-    const int r = idx / U, u = idx - r * U;
-    double2 v = make_double2(0.0, 0.0);
-    if (r < S) {
-      if (2 * u < S) v.x = __ldg(pm + r * S + 2 * u);
-      if (2 * u + 1 < S) v.y = __ldg(pm + r * S + 2 * u + 1);
+  if (op->kind[child] != SRC_TIP) {
+    for (int idx = threadIdx.x; idx < ROWS * U; idx += blockDim.x) {
+      const int r = idx / U, u = idx - r * U;
+      double2 v = make_double2(0.0, 0.0);
+      if (r < S) {
+        if (2 * u < S) v.x = __ldg(pm + r * S + 2 * u);
+        if (2 * u + 1 < S) v.y = __ldg(pm + r * S + 2 * u + 1);
+      }
+      dst[r * U + (((2 * u) ^ rc_swz<Cfg::SWZ_HALF>(r)) >> 1)] = v;
     }
-    dst[r * U + (((2 * u) ^ rc_swz<Cfg::SWZ_HALF>(r)) >> 1)] = v;
+    return;
+  }
+  for (int idx = threadIdx.x; idx < ROWS * U; idx += blockDim.x) {
+    const int r = idx / U, u = idx - r * U;   // row = tip code, columns = states 2u, 2u + 1
+    double v[2] = {0.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * u + e;
+      if (i >= S) continue;
+      const double* row = pm + i * S;
+      if (r < S) {
+        v[e] = __ldg(row + r);
+      } else if (r == S) {
+        double s = 0.0;
+        for (int j = 0; j < S; ++j) s += __ldg(row + j);
+        v[e] = s;
+      } else if (r - S < k.n_amb) {
+        const double* am = k.amb + (int64_t)(r - S) * S;
+        double s = 0.0;
+        for (int j = 0; j < S; ++j) s = fma(__ldg(row + j), __ldg(am + j), s);
+        v[e] = s;
+      }
+    }
+    dst[r * U + (u ^ (Cfg::SWZ_HALF ? (r & 1) << 2 : 0))] = make_double2(v[0], v[1]);
   }
 }
 
@@ -140,65 +183,42 @@ __device__ __forceinline__ void rc_load_codes(int (&cd)[2], const void* src, int
                               : (int)__ldg(static_cast<const uint16_t*>(src) + wsite + 8 * m);
 }
 
-// A tip child: acc (x)= P[state][code] per site (column gather of the staged matrix), row sums for '?' / '-'
-// cells, a dense dot for other ambiguity sets.  MUL: multiply into acc instead of overwriting it.
+// A tip child: acc (x)= the row of the transposed image selected by the site's code (a state, the all-ones set or
+// another ambiguity set), two states per 16-byte load.  MUL: multiply into acc instead of overwriting it.
 template <int S, bool MUL>
-__device__ __forceinline__ void rc_tip_child(double (&acc)[2][RcCfg<S>::NT][2], const double* Pm, const int (&cd)[2], int g,
-                                             int t4, const LaunchConst& k) {
-  constexpr int NT = RcCfg<S>::NT, PS = RcCfg<S>::PS;
+__device__ __forceinline__ void rc_tip_child(double (&acc)[2][RcCfg<S>::NT][2], const double* Pm, const int (&cd)[2], int t4,
+                                             const LaunchConst& k) {
+  constexpr int NT = RcCfg<S>::NT, PS = RcCfg<S>::PS, ROWS = RcCfg<S>::ROWS;
   constexpr bool HALF = RcCfg<S>::SWZ_HALF;
-  // swizzle of this thread's rows 8n + 2*t4 + e
-  const int sw[2] = {rc_swz<HALF>(2 * t4), rc_swz<HALF>(2 * t4 + 1)};
-  if (!__any_sync(0xffffffffu, cd[0] >= S || cd[1] >= S)) {
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
+  for (int m = 0; m < 2; ++m) {
+    const int row = cd[m];
+    if (row < ROWS) {
+      const double* rp = Pm + row * PS + 2 * t4;
+      const int par = HALF ? (row & 1) : 0;   // odd rows keep their 64-byte halves swapped
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const double* colp = Pm + (2 * t4 + e) * PS + (cd[m] ^ sw[e]);
+      for (int n = 0; n < NT; ++n) {
+        const double2 v = *reinterpret_cast<const double2*>(rp + 8 * (n ^ par));
+        acc[m][n][0] = MUL ? acc[m][n][0] * v.x : v.x;
+        acc[m][n][1] = MUL ? acc[m][n][1] * v.y : v.y;
+      }
+    } else {
+      // more ambiguity sets than spare rows: dense dot of the transposed columns with the 0/1 membership vector
+      const double* am = k.amb + (int64_t)(row - S) * S;
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-          const double v = colp[(8 * n) * PS];
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double v = 0.0;
+#pragma unroll 1
+          for (int j = 0; j < S; ++j) {
+            const int col = (8 * n + 2 * t4 + e) ^ ((HALF && (j & 1)) ? 8 : 0);
+            v = fma(Pm[j * PS + col], __ldg(am + j), v);
+          }
           acc[m][n][e] = MUL ? acc[m][n][e] * v : v;
         }
-      }
     }
-    return;
   }
-  // row sums of P: lane group g adds columns [8g, 8g + 8) of this thread's rows, a butterfly over the
-  // groups completes them (commutative pairs: identical in every lane)
-#pragma unroll
-  for (int n = 0; n < NT; ++n)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const double* row = Pm + (8 * n + 2 * t4 + e) * PS;
-      double s = 0.0;
-      if (g < NT) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {  // units of this lane group's 8 columns, swizzled: no two lanes of a quad collide
-          const double2 v = *reinterpret_cast<const double2*>(row + ((8 * g + 2 * r) ^ sw[e]));
-          s += v.x;
-          s += v.y;
-        }
-      }
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      s += __shfl_xor_sync(0xffffffffu, s, 8);
-      s += __shfl_xor_sync(0xffffffffu, s, 16);
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        double v;
-        if (cd[m] < S) {
-          v = row[cd[m] ^ sw[e]];
-        } else if (cd[m] == S) {
-          v = s;
-        } else {  // other ambiguity sets: dense dot with the 0/1 membership vector
-          const double* am = k.amb + (int64_t)(cd[m] - S) * S;
-          v = 0.0;
-#pragma unroll 1
-          for (int j = 0; j < S; ++j) v = fma(row[j ^ sw[e]], __ldg(am + j), v);
-        }
-        acc[m][n][e] = MUL ? acc[m][n][e] * v : v;
-      }
-    }
 }
 
 // acc = cur (16 sites x S, A fragments in registers) @ P^T (B fragments from the stage).
@@ -340,6 +360,8 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
     }
   };
 
+  int cdn[2] = {0, 0};   // tip codes of the NEXT op's first child, requested while this op rescales (when its stage is in)
+  bool have_cdn = false;
   int st = 0, round = 0, q = 0;
 #pragma unroll 1
   for (int o = rg.begin; o < rg.end; ++o) {
@@ -370,9 +392,9 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
       }
     }
     if (kind0 == SRC_TIP) {
-      int cd0[2];
-      rc_load_codes<S>(cd0, d->src[first], wsite, k.code_bytes);
-      rc_tip_child<S, false>(acc, Pm, cd0, g, t4, k);
+      int cd0[2] = {cdn[0], cdn[1]};
+      if (!have_cdn) rc_load_codes<S>(cd0, d->src[first], wsite, k.code_bytes);
+      rc_tip_child<S, false>(acc, Pm, cd0, t4, k);
     } else {
       if (kind0 == SRC_BUFFER) {
         rc_load_buffer<S>(cur, e_sum, d->src[first], d->src_scale[first], c, P, wsite, t4);
@@ -390,7 +412,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
     rc_mbar_wait(full_bar + st, (unsigned)(round & 1));
     if (lag_wait) rc_mbar_wait(lag_bar + st, (unsigned)(round & 1));
     if (kind1 == SRC_TIP) {
-      rc_tip_child<S, true>(acc, Pm, cd1, g, t4, k);
+      rc_tip_child<S, true>(acc, Pm, cd1, t4, k);
     } else {
       double acc2[2][NT][2];
       rc_load_buffer<S>(cur, e_sum, src1, scale1, c, P, wsite, t4);
@@ -403,6 +425,16 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
     release(st, q);
     ++q;
     if (++st == NST) { st = 0; ++round; }
+    // a look at the next op: if its first stage has landed and starts with a tip, request the codes now
+    have_cdn = false;
+    if (o + 1 < rg.end && __all_sync(0xffffffffu, rc_mbar_test(full_bar + st, (unsigned)(round & 1)))) {
+      const OpDesc* d2 = reinterpret_cast<const OpDesc*>(rsm + (size_t)st * Cfg::STAGE_D + Cfg::MAT_D);
+      const int f2 = (d2->kind[1] == SRC_CARRIED) ? 1 : 0;
+      if (d2->kind[f2] == SRC_TIP) {
+        rc_load_codes<S>(cdn, d2->src[f2], wsite, k.code_bytes);
+        have_cdn = true;
+      }
+    }
 
     // ---- rescale, store; the result stays in registers as the carried partial --------------------
 #pragma unroll

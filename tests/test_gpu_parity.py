@@ -95,7 +95,7 @@ def test_golden_full_and_dirty(name, golden_cases, gpu_backend):
     assert l3 == lnl
 
 
-def _random_problem(seed, n_taxa, n_sites, S, n_cats=4, missing=0.1, poly=0.02, bl_mean=0.1):
+def _random_problem(seed, n_taxa, n_sites, S, n_cats=4, missing=0.1, poly=0.02, bl_mean=0.1, n_poly=3):
     rng = np.random.default_rng(seed)
     pyr = random.Random(seed)
     # random topology: join two random subtrees until one is left; ids like the reference
@@ -113,7 +113,7 @@ def _random_problem(seed, n_taxa, n_sites, S, n_cats=4, missing=0.1, poly=0.02, 
     edges = oracle.edge_order(tree, root, n_taxa)
     amb = [np.ones(S)]
     if S > 2 and poly > 0:
-        for _ in range(3):
+        for _ in range(n_poly):
             v = np.zeros(S)
             v[rng.choice(S, size=2, replace=False)] = 1.0
             amb.append(v)
@@ -152,18 +152,24 @@ def test_random_inputs_vs_oracle(S, n_taxa, n_sites, model, gpu_backend):
                                                     (64, 33, 1000, "F81")])
 def test_random_inputs_register_carried_dmma(S, n_taxa, n_sites, model, gpu_backend, monkeypatch):
     """The same checks with the large-alignment FP64 tensor kernel (kernels_dmma_rc.cuh: partial carried in
-    mma fragments, P matrices streamed by a producer warp) forced onto small inputs: ragged last blocks
+    mma fragments, P matrices streamed by bulk-async copies) forced onto small inputs: ragged last blocks
     (64 of 128 sites), padded state counts (47), missing cells and ambiguity sets in every tile."""
     monkeypatch.setenv("CYBAYES_DMMA_RC", "1")
     _check_random_inputs(S, n_taxa, n_sites, model)
 
 
-def _check_random_inputs(S, n_taxa, n_sites, model):
+def test_register_carried_dmma_many_ambiguity_sets(gpu_backend, monkeypatch):
+    """More ambiguity sets than the spare rows of a staged tip image (8): codes beyond them take the dense path."""
+    monkeypatch.setenv("CYBAYES_DMMA_RC", "1")
+    _check_random_inputs(64, 9, 200, "GTR", n_poly=13, poly=0.2)
+
+
+def _check_random_inputs(S, n_taxa, n_sites, model, **problem):
     from cybayes_b200 import _lib
     from cybayes_b200.engine import Engine
     from cybayes_b200.likelihood import _Plan
     from cybayes_b200.subst import gtr_eigensystem
-    tree, root, edges, codes, amb, pi, er, rates = _random_problem(1000 + S, n_taxa, n_sites, S)
+    tree, root, edges, codes, amb, pi, er, rates = _random_problem(1000 + S, n_taxa, n_sites, S, **problem)
     C = len(rates)
     leaves = _oracle_leaves(codes, S, amb)
     beta = oracle.f81_beta(pi)
