@@ -97,7 +97,7 @@ static int load_nccl() {
 enum { NCCL_DOUBLE = 8, NCCL_SUM = 0 };  // ncclFloat64 / ncclSum in nccl.h
 
 // ------------------------------------------------------------------------------ context
-constexpr int64_t DMMA_RC_MIN_SITES = 16384;  // below this 128-site blocks x C cannot fill 148 SMs
+constexpr int64_t DMMA_RC_MIN_SITES = 1024;  // measured crossover against the 64-site tile kernel + level schedule (S = 47, 64)
 
 struct Buffer {
   double* data = nullptr;
@@ -230,8 +230,10 @@ static int create_impl(int device, cb_ctx** out) {
 #define CB_DMMA_ATTR(SS) CU(cudaFuncSetAttribute(prune_dmma_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
   CB_DMMA_ATTR(0); CB_DMMA_ATTR(32); CB_DMMA_ATTR(40); CB_DMMA_ATTR(47); CB_DMMA_ATTR(48); CB_DMMA_ATTR(56); CB_DMMA_ATTR(64);
 #undef CB_DMMA_ATTR
-#define CB_RC_ATTR(SS) CU(cudaFuncSetAttribute(prune_dmma_rc_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RcCfg<SS>::SMEM))
-  CB_RC_ATTR(32); CB_RC_ATTR(40); CB_RC_ATTR(47); CB_RC_ATTR(48); CB_RC_ATTR(56); CB_RC_ATTR(64);
+#define CB_RC_ATTR(SS)                                                                                                          \
+  CU(cudaFuncSetAttribute(prune_dmma_rc_kernel<SS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RcCfg<SS>::SMEM)); \
+  CU(cudaFuncSetAttribute(prune_dmma_rc_kernel<SS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RcCfg<SS>::SMEM))
+  CB_RC_ATTR(32); CB_RC_ATTR(40); CB_RC_ATTR(48); CB_RC_ATTR(56); CB_RC_ATTR(64);
 #undef CB_RC_ATTR
   if (const char* v = getenv("CYBAYES_RC_STAGGER")) c->rc_stagger = atoi(v) != 0;
   *out = c;
@@ -365,10 +367,12 @@ static int set_tips_impl(cb_ctx* c, int n_taxa, int64_t n_sites, int n_states, i
   c->use_dmma = !c->family_s2 && n_states >= 32 && n_states <= 64 && !getenv("CYBAYES_NO_DMMA");
   {
     // The kernel is fixed per alignment (never per schedule), so every evaluation of an alignment sums in one order.
-    // The register-carried variant needs 128-site blocks x C to fill the GPU: large alignments only (CYBAYES_DMMA_RC=1/0 forces).
-    const bool ct = n_states == 32 || n_states == 40 || n_states == 47 || n_states == 48 || n_states == 56 || n_states == 64;
+    // The register-carried variant (always with the walk schedule, cut into parallel subtrees when there are few site
+    // tiles) wins from ~1k patterns up: 0.37 vs 0.54 ms at 2048 x 94 taxa, 10.0 vs 18.5 ms at 16384 x 512 taxa (S = 64).
+    // CYBAYES_DMMA_RC=1/0 forces it on / off, CYBAYES_RC_MIN_SITES moves the threshold.
     const char* v = getenv("CYBAYES_DMMA_RC");
-    c->dmma_rc = c->use_dmma && ct && (v ? atoi(v) != 0 : c->P >= DMMA_RC_MIN_SITES);
+    const char* m = getenv("CYBAYES_RC_MIN_SITES");
+    c->dmma_rc = c->use_dmma && (v ? atoi(v) != 0 : c->P >= (m ? atoll(m) : DMMA_RC_MIN_SITES));
   }
   const int64_t P = c->P;
   if (dev_alloc(c, &c->d_codes, (size_t)n_taxa * P * code_bytes)) return 1;
@@ -742,9 +746,13 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
 #undef CB_LAUNCH_S2
   } else if (c->dmma_rc) {
     dim3 grid((unsigned)((c->P + RC_T - 1) / RC_T), (unsigned)n_r, (unsigned)c->n_cats);
-    switch (c->n_states) {
-#define CB_RC_CASE(SS) case SS: prune_dmma_rc_kernel<SS><<<grid, RC_THREADS, RcCfg<SS>::SMEM, c->stream>>>(kk); break
-      CB_RC_CASE(32); CB_RC_CASE(40); CB_RC_CASE(47); CB_RC_CASE(48); CB_RC_CASE(56); CB_RC_CASE(64);
+    switch ((c->n_states + 7) / 8 * 8) {  // compiled per padded state count; the real one is a run-time value
+#define CB_RC_CASE(SS)                                                                                          \
+  case SS:                                                                                                      \
+    if (c->n_states == SS) prune_dmma_rc_kernel<SS, true><<<grid, RC_THREADS, RcCfg<SS>::SMEM, c->stream>>>(kk); \
+    else prune_dmma_rc_kernel<SS, false><<<grid, RC_THREADS, RcCfg<SS>::SMEM, c->stream>>>(kk);                  \
+    break
+      CB_RC_CASE(32); CB_RC_CASE(40); CB_RC_CASE(48); CB_RC_CASE(56); CB_RC_CASE(64);
 #undef CB_RC_CASE
       default: return fail("internal error: no register-carried DMMA kernel for %d states", c->n_states);
     }
@@ -915,7 +923,8 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     REQUIRE(chain || n_lists == 1, "cb_eval_batch: candidate %d is not a chain of at most %d ops", li, MAX_CHAIN_OPS);
     Schedule sched = SCHED_CHAIN;
     if (!chain) {
-      const bool big = c->P >= (c->family_s2 ? WALK_MIN_SITES_S2 : WALK_MIN_SITES_GENERAL);
+      // the register-carried kernel only pays off when the partial is carried: its alignments always walk
+      const bool big = c->dmma_rc || c->P >= (c->family_s2 ? WALK_MIN_SITES_S2 : WALK_MIN_SITES_GENERAL);
       sched = ((big || (flags & CB_EVAL_FORCE_WALK)) && !(flags & CB_EVAL_FORCE_LEVELS)) ? SCHED_WALK : SCHED_LEVELS;
     }
 
@@ -1182,9 +1191,9 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   CU(cudaEventRecord(c->ev0, c->stream));
   if (c->dmma_rc) {
     const unsigned jobs = (unsigned)(total_ops * 2 * C);
-    switch (c->n_states) {
+    switch ((c->n_states + 7) / 8 * 8) {
 #define CB_RS_CASE(SS) case SS: rc_restage_kernel<SS><<<jobs, 256, 0, c->stream>>>(k, total_ops, c->d_staged); break
-      CB_RS_CASE(32); CB_RS_CASE(40); CB_RS_CASE(47); CB_RS_CASE(48); CB_RS_CASE(56); CB_RS_CASE(64);
+      CB_RS_CASE(32); CB_RS_CASE(40); CB_RS_CASE(48); CB_RS_CASE(56); CB_RS_CASE(64);
 #undef CB_RS_CASE
       default: return fail("internal error: no register-carried DMMA kernel for %d states", c->n_states);
     }

@@ -50,8 +50,11 @@ constexpr int RC_T = RC_WARPS * RC_WSITES;        // sites per block
 constexpr int RC_DESC_D = sizeof(OpDesc) / 8;     // doubles taken by the op descriptor copy of a stage
 constexpr int RC_EXTRA_ROWS = 8;                  // rows of a tip image beyond the padded states: codes S .. (row sums, ambiguity sets)
 
-template <int S> struct RcCfg {
-  static constexpr int S8 = (S + 7) / 8 * 8;
+// All kernels here are compiled per PADDED state count S8 (a multiple of 8: 32, 40, 48, 56, 64); the real state count
+// S (S8 - 8 < S <= S8) is a run-time value that only matters in the last state tile.
+template <int S8_> struct RcCfg {
+  static constexpr int S8 = S8_;
+  static_assert(S8 % 8 == 0, "padded state count");
   static constexpr int NT = S8 / 8;                                  // 8-state tiles (n tiles = k block pairs)
   static constexpr int PS = S8;                                      // P row stride in a stage (unpadded, swizzled)
   static constexpr bool SWZ_HALF = (S8 % 16 == 0);                   // rows start in the same 128-byte bank window
@@ -125,10 +128,11 @@ __device__ __forceinline__ void rc_dmma(double& c0, double& c1, double a, double
 //   tip child:       row r < S: P[.][r] (P transposed); row S: sum_j P[.][j]; row S + k: sum_j P[.][j] amb[k][j];
 //                    unit index ^= (r & 1) << 2 when rows are a multiple of 128 bytes (two sites' rows in different banks).
 // One block per matrix.
-template <int S>
+template <int S8>
 __global__ void __launch_bounds__(256) rc_restage_kernel(const LaunchConst k, int n_ops, double* __restrict__ staged) {
-  using Cfg = RcCfg<S>;
-  constexpr int S8 = Cfg::S8, U = S8 / 2, ROWS = Cfg::ROWS;   // U: 16-byte units per row
+  using Cfg = RcCfg<S8>;
+  constexpr int U = S8 / 2, ROWS = Cfg::ROWS;   // U: 16-byte units per row
+  const int S = k.n_states;
   const int job = blockIdx.x;               // (o * 2 + step) * C + c
   const int C = k.n_cats;
   const int c = job % C, os = job / C, step = os & 1, o = os >> 1;
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(256) rc_restage_kernel(const LaunchConst k, in
   }
 }
 
-template <int S>
+template <int S8>
 __device__ __forceinline__ void rc_load_codes(int (&cd)[2], const void* src, int64_t wsite, int code_bytes) {
 #pragma unroll
   for (int m = 0; m < 2; ++m)
@@ -185,11 +189,11 @@ __device__ __forceinline__ void rc_load_codes(int (&cd)[2], const void* src, int
 
 // A tip child: acc (x)= the row of the transposed image selected by the site's code (a state, the all-ones set or
 // another ambiguity set), two states per 16-byte load.  MUL: multiply into acc instead of overwriting it.
-template <int S, bool MUL>
-__device__ __forceinline__ void rc_tip_child(double (&acc)[2][RcCfg<S>::NT][2], const double* Pm, const int (&cd)[2], int t4,
-                                             const LaunchConst& k) {
-  constexpr int NT = RcCfg<S>::NT, PS = RcCfg<S>::PS, ROWS = RcCfg<S>::ROWS;
-  constexpr bool HALF = RcCfg<S>::SWZ_HALF;
+template <int S8, bool MUL>
+__device__ __forceinline__ void rc_tip_child(double (&acc)[2][RcCfg<S8>::NT][2], const double* Pm, const int (&cd)[2], int t4,
+                                             int S, const LaunchConst& k) {
+  constexpr int NT = RcCfg<S8>::NT, PS = RcCfg<S8>::PS, ROWS = RcCfg<S8>::ROWS;
+  constexpr bool HALF = RcCfg<S8>::SWZ_HALF;
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
     const int row = cd[m];
@@ -223,10 +227,10 @@ __device__ __forceinline__ void rc_tip_child(double (&acc)[2][RcCfg<S>::NT][2], 
 
 // acc = cur (16 sites x S, A fragments in registers) @ P^T (B fragments from the stage).
 // k blocks (j,0), (j,1) of one state tile come from a single conflict-free LDS.128.
-template <int S>
-__device__ __forceinline__ void rc_contract(double (&acc)[2][RcCfg<S>::NT][2], const double (&cur)[2][RcCfg<S>::NT][2],
+template <int S8>
+__device__ __forceinline__ void rc_contract(double (&acc)[2][RcCfg<S8>::NT][2], const double (&cur)[2][RcCfg<S8>::NT][2],
                                             const double* Pm, int g, int t4) {
-  constexpr int NT = RcCfg<S>::NT, PS = RcCfg<S>::PS;
+  constexpr int NT = RcCfg<S8>::NT, PS = RcCfg<S8>::PS;
 #pragma unroll
   for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -234,7 +238,7 @@ __device__ __forceinline__ void rc_contract(double (&acc)[2][RcCfg<S>::NT][2], c
   // B fragment of (state tile n, k pair j): row 8n + g, logical column 8j + 2*t4.  The row swizzle only depends
   // on g: (8j + 2 t4) ^ swz = 8 (j ^ hb) + ((2 t4) ^ lo), so two lane-constant bases (even / odd j) make every
   // address base + compile-time offset.
-  const int swg = rc_swz<RcCfg<S>::SWZ_HALF>(g);
+  const int swg = rc_swz<RcCfg<S8>::SWZ_HALF>(g);
   const int hb = (swg >> 3) & 1;
   const double* p_even = Pm + g * PS + ((2 * t4) ^ (swg & 7)) + 8 * hb;
   const double* p_odd = p_even - 16 * hb;
@@ -268,10 +272,10 @@ __device__ __forceinline__ void rc_contract(double (&acc)[2][RcCfg<S>::NT][2], c
 }
 
 // a stored partial -> A-fragment registers (+ its exponents): per request 4 rows x 64 contiguous bytes
-template <int S>
-__device__ __forceinline__ void rc_load_buffer(double (&cur)[2][RcCfg<S>::NT][2], int (&e_sum)[2], const void* src,
-                                               const int32_t* sscale, int c, int64_t P, int64_t wsite, int t4) {
-  constexpr int NT = RcCfg<S>::NT, S8 = RcCfg<S>::S8;
+template <int S8>
+__device__ __forceinline__ void rc_load_buffer(double (&cur)[2][RcCfg<S8>::NT][2], int (&e_sum)[2], const void* src,
+                                               const int32_t* sscale, int c, int S, int64_t P, int64_t wsite, int t4) {
+  constexpr int NT = RcCfg<S8>::NT;
   const double* sp = static_cast<const double*>(src) + (int64_t)c * S * P + wsite;
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
@@ -280,7 +284,7 @@ __device__ __forceinline__ void rc_load_buffer(double (&cur)[2][RcCfg<S>::NT][2]
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int stt = 8 * n + 2 * t4 + e;
-        cur[m][n][e] = (S8 == S || stt < S) ? __ldcg(sp + (int64_t)stt * P + 8 * m) : 0.0;
+        cur[m][n][e] = (n < NT - 1 || stt < S) ? __ldcg(sp + (int64_t)stt * P + 8 * m) : 0.0;
       }
     e_sum[m] += __ldcg(sscale + (int64_t)c * P + wsite + 8 * m);
   }
@@ -288,10 +292,10 @@ __device__ __forceinline__ void rc_load_buffer(double (&cur)[2][RcCfg<S>::NT][2]
 
 // Fill the stage of job q (= 2 * (op - begin) + step) of this block: re-arm its barrier with the byte count, then
 // the matrix in four bulk copies and, for a first child, the op descriptor.  Executed by ONE thread.
-template <int S>
+template <int S8>
 __device__ __forceinline__ void rc_issue_job(const LaunchConst& k, const RangeDesc& rg, int c, int q, double* rsm,
                                              unsigned long long* full_bar) {
-  using Cfg = RcCfg<S>;
+  using Cfg = RcCfg<S8>;
   const int st = q % Cfg::NST, step = q & 1, o = rg.begin + (q >> 1);
   double* stage = rsm + (size_t)st * Cfg::STAGE_D;
   const char* src = reinterpret_cast<const char*>(k.staged + ((int64_t)(o * 2 + step) * k.n_cats + c) * Cfg::MAT_D);
@@ -302,10 +306,12 @@ __device__ __forceinline__ void rc_issue_job(const LaunchConst& k, const RangeDe
   if (step == 0) rc_bulk_g2s(stage + Cfg::MAT_D, k.ops + o, (unsigned)sizeof(OpDesc), full_bar + st);
 }
 
-template <int S>
+// EXACT: the state count is S8 itself (a compile-time value: the padding guards of the last state tile fold away).
+template <int S8, bool EXACT>
 __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const LaunchConst k) {
-  using Cfg = RcCfg<S>;
-  constexpr int NT = Cfg::NT, NST = Cfg::NST, S8 = Cfg::S8;
+  using Cfg = RcCfg<S8>;
+  constexpr int NT = Cfg::NT, NST = Cfg::NST;
+  const int S = EXACT ? S8 : k.n_states;
   extern __shared__ __align__(128) double rsm[];
   unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(rsm + (size_t)NST * Cfg::STAGE_D);
   unsigned long long* lag_bar = full_bar + 8;                         // warps 0..3 have finished a stage
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
       done_cnt[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");   // barriers visible to the async proxy
-    for (int q = 0; q < NST && q < n_jobs; ++q) rc_issue_job<S>(k, rg, c, q, rsm, full_bar);
+    for (int q = 0; q < NST && q < n_jobs; ++q) rc_issue_job<S8>(k, rg, c, q, rsm, full_bar);
   }
   __syncthreads();  // the only block-wide barrier
   if (warp >= n_active) return;
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
         done_cnt[st] = 0;
         if (q + NST < n_jobs) {
           asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the warps' reads before the async writes
-          rc_issue_job<S>(k, rg, c, q + NST, rsm, full_bar);
+          rc_issue_job<S8>(k, rg, c, q + NST, rsm, full_bar);
         }
       }
     }
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
     int32_t* dst_scale = d->dst_scale;
     int cd1[2] = {0, 0};
     if (kind1 == SRC_TIP) {
-      rc_load_codes<S>(cd1, src1, wsite, k.code_bytes);  // in flight during the first child's contraction
+      rc_load_codes<S8>(cd1, src1, wsite, k.code_bytes);  // in flight during the first child's contraction
     } else {
       // the stored partial of the second child: pull its 16 sites x S doubles towards L2 now
       const char* sp = reinterpret_cast<const char*>(static_cast<const double*>(src1) + (int64_t)c * S * P + wsite - g);
@@ -393,16 +399,16 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
     }
     if (kind0 == SRC_TIP) {
       int cd0[2] = {cdn[0], cdn[1]};
-      if (!have_cdn) rc_load_codes<S>(cd0, d->src[first], wsite, k.code_bytes);
-      rc_tip_child<S, false>(acc, Pm, cd0, t4, k);
+      if (!have_cdn) rc_load_codes<S8>(cd0, d->src[first], wsite, k.code_bytes);
+      rc_tip_child<S8, false>(acc, Pm, cd0, t4, S, k);
     } else {
       if (kind0 == SRC_BUFFER) {
-        rc_load_buffer<S>(cur, e_sum, d->src[first], d->src_scale[first], c, P, wsite, t4);
+        rc_load_buffer<S8>(cur, e_sum, d->src[first], d->src_scale[first], c, S, P, wsite, t4);
       } else {
         e_sum[0] += cur_e[0];
         e_sum[1] += cur_e[1];
       }
-      rc_contract<S>(acc, cur, Pm, g, t4);
+      rc_contract<S8>(acc, cur, Pm, g, t4);
     }
     release(st, q);
     ++q;
@@ -412,11 +418,11 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
     rc_mbar_wait(full_bar + st, (unsigned)(round & 1));
     if (lag_wait) rc_mbar_wait(lag_bar + st, (unsigned)(round & 1));
     if (kind1 == SRC_TIP) {
-      rc_tip_child<S, true>(acc, Pm, cd1, t4, k);
+      rc_tip_child<S8, true>(acc, Pm, cd1, t4, S, k);
     } else {
       double acc2[2][NT][2];
-      rc_load_buffer<S>(cur, e_sum, src1, scale1, c, P, wsite, t4);
-      rc_contract<S>(acc2, cur, Pm, g, t4);
+      rc_load_buffer<S8>(cur, e_sum, src1, scale1, c, S, P, wsite, t4);
+      rc_contract<S8>(acc2, cur, Pm, g, t4);
 #pragma unroll
       for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -431,7 +437,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
       const OpDesc* d2 = reinterpret_cast<const OpDesc*>(rsm + (size_t)st * Cfg::STAGE_D + Cfg::MAT_D);
       const int f2 = (d2->kind[1] == SRC_CARRIED) ? 1 : 0;
       if (d2->kind[f2] == SRC_TIP) {
-        rc_load_codes<S>(cdn, d2->src[f2], wsite, k.code_bytes);
+        rc_load_codes<S8>(cdn, d2->src[f2], wsite, k.code_bytes);
         have_cdn = true;
       }
     }
@@ -465,7 +471,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int stt = 8 * n + 2 * t4 + e;
-            if (S8 == S || stt < S) __stcg(dp + (int64_t)stt * P, cur[m][n][e]);
+            if (n < NT - 1 || stt < S) __stcg(dp + (int64_t)stt * P, cur[m][n][e]);
           }
         if (t4 == 0) __stcg(dst_scale + (int64_t)c * P + site, cur_e[m]);
       }
@@ -476,7 +482,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) prune_dmma_rc_kernel(const Laun
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int stt = 8 * n + 2 * t4 + e;
-            const double pv = (S8 == S || stt < S) ? __ldg(k.pi + stt) : 0.0;
+            const double pv = (n < NT - 1 || stt < S) ? __ldg(k.pi + stt) : 0.0;
             dot = fma(pv, cur[m][n][e], dot);
           }
         dot += __shfl_xor_sync(0xffffffffu, dot, 1);

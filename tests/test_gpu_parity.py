@@ -149,7 +149,8 @@ def test_random_inputs_vs_oracle(S, n_taxa, n_sites, model, gpu_backend):
 
 @pytest.mark.parametrize("S,n_taxa,n_sites,model", [(64, 8, 100, "GTR"), (47, 10, 64, "GTR"), (40, 7, 90, "GTR"),
                                                     (32, 9, 300, "F81"), (56, 12, 200, "JC"), (48, 6, 129, "GTR"),
-                                                    (64, 33, 1000, "F81")])
+                                                    (64, 33, 1000, "F81"), (33, 7, 70, "GTR"), (46, 8, 130, "F81"),
+                                                    (61, 6, 100, "JC")])
 def test_random_inputs_register_carried_dmma(S, n_taxa, n_sites, model, gpu_backend, monkeypatch):
     """The same checks with the large-alignment FP64 tensor kernel (kernels_dmma_rc.cuh: partial carried in
     mma fragments, P matrices streamed by bulk-async copies) forced onto small inputs: ragged last blocks
