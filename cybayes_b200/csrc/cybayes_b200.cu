@@ -97,6 +97,7 @@ static int load_nccl() {
 enum { NCCL_DOUBLE = 8, NCCL_SUM = 0 };  // ncclFloat64 / ncclSum in nccl.h
 
 // ------------------------------------------------------------------------------ context
+constexpr int DMMA_RC_MIN_STATES = 9;   // measured: 1.65x (S = 23, 2304 patterns) .. 3.1x (S = 30, 16384) over the plain FP64 kernel
 constexpr int64_t DMMA_RC_MIN_SITES = 1024;  // measured crossover against the 64-site tile kernel + level schedule (S = 47, 64)
 
 struct Buffer {
@@ -233,7 +234,7 @@ static int create_impl(int device, cb_ctx** out) {
 #define CB_RC_ATTR(SS)                                                                                                          \
   CU(cudaFuncSetAttribute(prune_dmma_rc_kernel<SS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RcCfg<SS>::SMEM)); \
   CU(cudaFuncSetAttribute(prune_dmma_rc_kernel<SS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RcCfg<SS>::SMEM))
-  CB_RC_ATTR(32); CB_RC_ATTR(40); CB_RC_ATTR(48); CB_RC_ATTR(56); CB_RC_ATTR(64);
+  CB_RC_ATTR(16); CB_RC_ATTR(24); CB_RC_ATTR(32); CB_RC_ATTR(40); CB_RC_ATTR(48); CB_RC_ATTR(56); CB_RC_ATTR(64);
 #undef CB_RC_ATTR
   if (const char* v = getenv("CYBAYES_RC_STAGGER")) c->rc_stagger = atoi(v) != 0;
   *out = c;
@@ -372,7 +373,10 @@ static int set_tips_impl(cb_ctx* c, int n_taxa, int64_t n_sites, int n_states, i
     // CYBAYES_DMMA_RC=1/0 forces it on / off, CYBAYES_RC_MIN_SITES moves the threshold.
     const char* v = getenv("CYBAYES_DMMA_RC");
     const char* m = getenv("CYBAYES_RC_MIN_SITES");
-    c->dmma_rc = c->use_dmma && (v ? atoi(v) != 0 : c->P >= (m ? atoll(m) : DMMA_RC_MIN_SITES));
+    const char* ms = getenv("CYBAYES_RC_MIN_STATES");
+    const bool states_ok = !c->family_s2 && n_states >= (ms ? std::max(9, atoi(ms)) : DMMA_RC_MIN_STATES) && n_states <= 64 &&
+                           !getenv("CYBAYES_NO_DMMA");
+    c->dmma_rc = states_ok && (v ? atoi(v) != 0 : c->P >= (m ? atoll(m) : DMMA_RC_MIN_SITES));
   }
   const int64_t P = c->P;
   if (dev_alloc(c, &c->d_codes, (size_t)n_taxa * P * code_bytes)) return 1;
@@ -752,7 +756,7 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
     if (c->n_states == SS) prune_dmma_rc_kernel<SS, true><<<grid, RC_THREADS, RcCfg<SS>::SMEM, c->stream>>>(kk); \
     else prune_dmma_rc_kernel<SS, false><<<grid, RC_THREADS, RcCfg<SS>::SMEM, c->stream>>>(kk);                  \
     break
-      CB_RC_CASE(32); CB_RC_CASE(40); CB_RC_CASE(48); CB_RC_CASE(56); CB_RC_CASE(64);
+      CB_RC_CASE(16); CB_RC_CASE(24); CB_RC_CASE(32); CB_RC_CASE(40); CB_RC_CASE(48); CB_RC_CASE(56); CB_RC_CASE(64);
 #undef CB_RC_CASE
       default: return fail("internal error: no register-carried DMMA kernel for %d states", c->n_states);
     }
@@ -1193,7 +1197,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     const unsigned jobs = (unsigned)(total_ops * 2 * C);
     switch ((c->n_states + 7) / 8 * 8) {
 #define CB_RS_CASE(SS) case SS: rc_restage_kernel<SS><<<jobs, 256, 0, c->stream>>>(k, total_ops, c->d_staged); break
-      CB_RS_CASE(32); CB_RS_CASE(40); CB_RS_CASE(48); CB_RS_CASE(56); CB_RS_CASE(64);
+      CB_RS_CASE(16); CB_RS_CASE(24); CB_RS_CASE(32); CB_RS_CASE(40); CB_RS_CASE(48); CB_RS_CASE(56); CB_RS_CASE(64);
 #undef CB_RS_CASE
       default: return fail("internal error: no register-carried DMMA kernel for %d states", c->n_states);
     }

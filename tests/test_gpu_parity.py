@@ -159,6 +159,15 @@ def test_random_inputs_register_carried_dmma(S, n_taxa, n_sites, model, gpu_back
     _check_random_inputs(S, n_taxa, n_sites, model)
 
 
+@pytest.mark.parametrize("S,n_taxa,n_sites,model", [(23, 14, 129, "JC"), (9, 5, 70, "GTR"), (17, 6, 200, "F81"),
+                                                    (31, 7, 90, "GTR"), (16, 9, 64, "F81"), (24, 5, 300, "GTR")])
+def test_register_carried_dmma_small_state_counts(S, n_taxa, n_sites, model, gpu_backend, monkeypatch):
+    """The register-carried kernel compiled for 16 and 24 padded states (9 <= S < 32)."""
+    monkeypatch.setenv("CYBAYES_DMMA_RC", "1")
+    monkeypatch.setenv("CYBAYES_RC_MIN_STATES", "9")
+    _check_random_inputs(S, n_taxa, n_sites, model)
+
+
 def test_register_carried_dmma_many_ambiguity_sets(gpu_backend, monkeypatch):
     """More ambiguity sets than the spare rows of a staged tip image (8): codes beyond them take the dense path."""
     monkeypatch.setenv("CYBAYES_DMMA_RC", "1")
