@@ -315,6 +315,11 @@ def run_ours(a):
                 "traffic": traffic, "kernel": "prune_s2_kernel<4>", "algorithmic_bytes_per_eval": alg_bytes,
                 "kernel_ms_per_eval": k_ms, "peak_source": peak_src,
                 "launches_per_eval": (st1["kernel_launches"] - st0["kernel_launches"]) / a.steps}
+    if traffic is not None:
+        # the walk never writes carried / folded partials, so it moves fewer bytes than the algorithmic count: the
+        # bandwidth it actually draws (ncu DRAM bytes of this kernel / this run's kernel time) against the same peak
+        roofline["traffic_GBps"] = traffic / (k_ms * 1e-3) / 1e9
+        roofline["traffic_frac"] = roofline["traffic_GBps"] / peak
 
     # end to end through the reference-facing call: host P matrices (numpy, one dict per category) ->
     # matML -> float.  Timed region holds the H2D of P matrices + op descriptors and the D2H of lnL.
