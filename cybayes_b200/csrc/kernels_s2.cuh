@@ -84,6 +84,7 @@ template <> struct VecD<1> {
   __device__ __forceinline__ void load(const double* p) { v[0] = __ldcg(p); }
   __device__ __forceinline__ void load_ca(const double* p) { v[0] = __ldca(p); }
   __device__ __forceinline__ void store(double* p) const { __stcg(p, v[0]); }
+  __device__ __forceinline__ void store_cs(double* p) const { __stcs(p, v[0]); }
 };
 template <> struct VecD<2> {
   double v[2];
@@ -92,6 +93,7 @@ template <> struct VecD<2> {
     const double2 t = __ldca(reinterpret_cast<const double2*>(p)); v[0] = t.x; v[1] = t.y;
   }
   __device__ __forceinline__ void store(double* p) const { st_cg2(p, make_double2(v[0], v[1])); }
+  __device__ __forceinline__ void store_cs(double* p) const { __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1])); }
 };
 template <int V> __device__ __forceinline__ void load_ints(const int32_t* p, int (&e)[V]);
 template <> __device__ __forceinline__ void load_ints<1>(const int32_t* p, int (&e)[1]) { e[0] = __ldcg(p); }
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
       r.ctip[0][0] = op->ctip[0][0]; r.ctip[0][1] = op->ctip[0][1];
       r.ctip[1][0] = op->ctip[1][0]; r.ctip[1][1] = op->ctip[1][1];
       r.kind[0] = op->kind[0]; r.kind[1] = op->kind[1];
-      r.is_root = op->is_root; r.pad_ = 0;
+      r.is_root = op->is_root; r.pad_ = op->pad_;
       st[o] = r;
     }
     // ... the P matrices of internal and tip children (one thread per category and row) ...
@@ -397,10 +399,18 @@ __global__ void __launch_bounds__(THREADS, MINB) prune_s2_kernel(const LaunchCon
         }
         if (op.dst != nullptr) {
           double* dst = op.dst + site;
+          if (op.pad_) {  // kept for the cache only: streaming stores leave L2 to the partials this walk reads back
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            cur[c][0].store(dst + (int64_t)(2 * c) * P);
-            cur[c][1].store(dst + (int64_t)(2 * c + 1) * P);
+            for (int c = 0; c < C; ++c) {
+              cur[c][0].store_cs(dst + (int64_t)(2 * c) * P);
+              cur[c][1].store_cs(dst + (int64_t)(2 * c + 1) * P);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              cur[c][0].store(dst + (int64_t)(2 * c) * P);
+              cur[c][1].store(dst + (int64_t)(2 * c + 1) * P);
+            }
           }
           store_ints<V>(op.dst_scale + site, cur_e);
         }
