@@ -20,8 +20,12 @@
 
 namespace cb {
 
+// A stored partial is read back at most once per evaluation: "last use" loads let L2 drop the line afterwards.
+#ifndef CB_LD_BUFFER
+#define CB_LD_BUFFER __ldlu
+#endif
 __device__ __forceinline__ double2 ld_cg2(const double* p) {
-  return __ldcg(reinterpret_cast<const double2*>(p));
+  return CB_LD_BUFFER(reinterpret_cast<const double2*>(p));
 }
 __device__ __forceinline__ void st_cg2(double* p, double2 v) {
   __stcg(reinterpret_cast<double2*>(p), v);
@@ -81,7 +85,7 @@ constexpr int S2_STAGE_OPS = 32;  // ops whose descriptors + P matrices / lookup
 template <int V> struct VecD;
 template <> struct VecD<1> {
   double v[1];
-  __device__ __forceinline__ void load(const double* p) { v[0] = __ldcg(p); }
+  __device__ __forceinline__ void load(const double* p) { v[0] = CB_LD_BUFFER(p); }
   __device__ __forceinline__ void load_ca(const double* p) { v[0] = __ldca(p); }
   __device__ __forceinline__ void store(double* p) const { __stcg(p, v[0]); }
   __device__ __forceinline__ void store_cs(double* p) const { __stcs(p, v[0]); }
@@ -96,7 +100,7 @@ template <> struct VecD<2> {
   __device__ __forceinline__ void store_cs(double* p) const { __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1])); }
 };
 template <int V> __device__ __forceinline__ void load_ints(const int32_t* p, int (&e)[V]);
-template <> __device__ __forceinline__ void load_ints<1>(const int32_t* p, int (&e)[1]) { e[0] = __ldcg(p); }
+template <> __device__ __forceinline__ void load_ints<1>(const int32_t* p, int (&e)[1]) { e[0] = CB_LD_BUFFER(p); }
 template <> __device__ __forceinline__ void load_ints<2>(const int32_t* p, int (&e)[2]) {
   const int2 t = __ldcg(reinterpret_cast<const int2*>(p)); e[0] = t.x; e[1] = t.y;
 }
