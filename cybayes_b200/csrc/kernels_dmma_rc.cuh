@@ -38,7 +38,6 @@
 // one block per SM.
 #pragma once
 #include "cb_types.cuh"
-#include "kernels_dmma.cuh"
 #include "kernels_s2.cuh"
 
 namespace cb {
