@@ -26,7 +26,7 @@ import numpy as np
 
 from . import config, utils
 from .ML_gamma import cache_matML, matML
-from .subst import get_edge_transition_mats
+from .subst import get_edge_transition_mats, get_prob_t_all
 from .mcmc_gamma import (adjlist2newickBL, adjlist2nodes_dict, adjlist2reverse_nodes_dict, externalSPR,
                          get_edge_transition_mat, get_path2root, get_prob_t, get_siterates, mvDualSlider,
                          node_slider, rooted_NNI, scale_alpha, scale_edge, state_init)
@@ -204,7 +204,7 @@ def run_chain(input_file, model, n_gen, thin, data_type, output_file, reader=Non
                 proposed_ll, proposed_cache = cache_matML(pi_prop, root, leaves, cache, [root], order_prop,
                                                           prop_tmats, n_sites, n_taxa, n_cats)
         else:
-            prop_tmats = [get_prob_t(pi_prop, tree_prop, rates_prop, r) for r in site_rates]
+            prop_tmats = get_prob_t_all(pi_prop, tree_prop, rates_prop, site_rates)
             proposed_ll, proposed_cache = matML(pi_prop, root, leaves, order_prop, prop_tmats, n_sites, n_taxa, n_cats)
 
         current_ll = state["logLikehood"]

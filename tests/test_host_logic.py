@@ -260,3 +260,21 @@ def test_unmodified_non_gamma_driver_on_compat_modules(name, fname, model, dtype
                                             "-n", str(n_gen), "-t", "1", "-d", dtype, "-o", str(tmp_path / "ng")],
                                monkeypatch, capsys)
     check_nongamma_trace(out, name, 1e-10)
+
+
+def test_siterates_direct_quantile_is_bit_identical():
+    """get_siterates calls scipy.special.chdtri instead of chi2.isf (same function under ~100 us of argument
+    checking): the four category rates must keep the reference's bits (mcmc_gamma.pyx:596-602)."""
+    from scipy.special import gammainc
+    from scipy.stats import chi2
+    from cybayes_b200 import config
+    from cybayes_b200.subst import get_siterates
+    config.N_CATS = 4
+    rng = np.random.default_rng(11)
+    for a in np.concatenate([rng.uniform(0.01, 5, 3000), rng.uniform(5, 200, 500), [1e-3, 0.6863337793704655, 1000.0]]):
+        alpha = float(np.float32(a))
+        cut = [chi2.isf(1 - p, 2 * alpha) for p in np.arange(0.25, 1, 0.25)]
+        cum = [gammainc(alpha + 1, c * alpha) for c in cut]
+        want = [cum[0] * 4, (cum[1] - cum[0]) * 4, (cum[2] - cum[1]) * 4, (1.0 - cum[2]) * 4]
+        got = get_siterates(a)
+        assert [float(x) for x in got] == [float(x) for x in want], (a, got, want)
