@@ -142,7 +142,7 @@ def reset_engines():
 class _Plan:
     """Edge list -> node operations.  `nodes[i]` is completed by the i-th op in the order in
     which the reference finishes parents while walking `edges` (ML_gamma.pyx:24-36)."""
-    __slots__ = ("edges", "node_list", "kids", "index", "_nodes", "_children", "_edge_keys")
+    __slots__ = ("edges", "node_list", "kids", "index", "_nodes", "_children", "_edge_keys", "_paths")
 
     def __init__(self, edges):
         self.edges = list(edges)
@@ -160,6 +160,7 @@ class _Plan:
         self.kids, self.node_list = kids, node_list
         self.index = dict(zip(node_list, range(len(node_list))))
         self._nodes = self._children = self._edge_keys = None
+        self._paths = {}   # dirty set -> (nodes, children, edge keys, getter): the same few paths recur while a tree lives
 
     @property
     def nodes(self):
@@ -197,11 +198,12 @@ def _plan_for(edges):
     return p
 
 
-def _slot_matrix(engine, tmats, edge_keys):
+def _slot_matrix(engine, tmats, edge_keys, getter=None):
     """(n_edges, C) int32 P-slot table for the ops' edges.  Device tables are looked up; reference-style
     host dicts of ndarrays are uploaded (host buffers -> one H2D copy per category) in op order."""
     cols = []
-    getter = itemgetter(*edge_keys) if len(edge_keys) > 1 else (lambda d: (d[edge_keys[0]],))
+    if getter is None:
+        getter = itemgetter(*edge_keys) if len(edge_keys) > 1 else (lambda d: (d[edge_keys[0]],))
     keep = []
     n = len(edge_keys)
     S = engine.n_states
@@ -329,14 +331,22 @@ def _dirty(pi, root, ll_mats, cache, nodes_recompute, edges, tmats, n_cats_table
     if not isinstance(cache, PartialCache) or cache.engine is not engine:
         raise TypeError("cache_LL_Mats must be the cache returned by matML/cache_matML for this alignment")
     plan = _plan_for(edges)
-    index, kids = plan.index, plan.kids
-    todo = sorted(set(nodes_recompute), key=index.__getitem__)
-    if not todo or todo[-1] != root:
-        todo = sorted(set(todo) | {root}, key=index.__getitem__)  # the root partial is never cached
-    nodes = np.array(todo, dtype=np.int32)
-    children = np.array([c for n in todo for c in kids[n]], dtype=np.int32)
-    edge_keys = [(n, c) for n in todo for c in kids[n]]
-    pslots, keep = _slot_matrix(engine, tmats, edge_keys)
+    key = (root,) + tuple(nodes_recompute)
+    hit = plan._paths.get(key)
+    if hit is None:
+        index, kids = plan.index, plan.kids
+        todo = sorted(set(nodes_recompute), key=index.__getitem__)
+        if not todo or todo[-1] != root:
+            todo = sorted(set(todo) | {root}, key=index.__getitem__)  # the root partial is never cached
+        edge_keys = [(n, c) for n in todo for c in kids[n]]
+        hit = plan._paths[key] = (np.array(todo, dtype=np.int32),
+                                  np.array([c for n in todo for c in kids[n]], dtype=np.int32), edge_keys,
+                                  itemgetter(*edge_keys) if len(edge_keys) > 1 else None)
+        if len(plan._paths) > 512:
+            plan._paths.clear()
+            plan._paths[key] = hit
+    nodes, children, edge_keys, getter = hit
+    pslots, keep = _slot_matrix(engine, tmats, edge_keys, getter)
     lnl, snap = engine.eval(cache.snap, nodes, children, pslots, np.asarray(pi, dtype=np.float64),
                             want_snapshot=True, store_root=STORE_ROOT)
     return np.float64(lnl), PartialCache(engine, snap, site_map, cache.nodes())
