@@ -278,3 +278,55 @@ def test_siterates_direct_quantile_is_bit_identical():
         want = [cum[0] * 4, (cum[1] - cum[0]) * 4, (cum[2] - cum[1]) * 4, (1.0 - cum[2]) * 4]
         got = get_siterates(a)
         assert [float(x) for x in got] == [float(x) for x in want], (a, got, want)
+
+
+@pytest.mark.parametrize("name", ["narrow_F81", "phon_ringe_JC", "phon_ringe_GTR"])
+def test_get_prob_t_all_equals_per_category_calls(name, golden_cases, fake_backend):
+    """The restated driver's one-entry builder for all rate categories must give the matrices of the reference's
+    per-category get_prob_t calls (mat_mcmc_gamma.py:147) and keep its shared slot block alive per table."""
+    from cybayes_b200 import config
+    from cybayes_b200.driver import load_alignment
+    from cybayes_b200.subst import get_prob_t, get_prob_t_all
+    case = golden_cases[name]
+    load_alignment(golden_io.data_path(case), case["dtype"], case["reader"])
+    config.MODEL, config.NORM_BETA = case["model"], case["norm_beta"]
+    tree, pi, rates, edges, site_rates = golden_io.case_state(case)
+    if rates is None:
+        rates = np.ones(1)
+    one_by_one = [get_prob_t(pi, tree, rates, r) for r in site_rates]
+    together = get_prob_t_all(pi, tree, rates, site_rates)
+    assert len(together) == len(one_by_one)
+    for a, b in zip(one_by_one, together):
+        assert list(a.keys()) == list(b.keys())
+        for e in list(tree)[::7]:
+            assert np.array_equal(np.asarray(a[e]), np.asarray(b[e]))
+    eng = together[0].engine
+    n = together[0]._block.n
+    first = together.pop(0)
+    del first
+    assert together[0]._block.base not in eng._free_slots.get(n, [])   # still referenced by the other tables
+    base = together[0]._block.base
+    del together, a, b
+    assert base in eng._free_slots.get(n, [])
+
+
+def test_dirty_path_op_lists_are_cached_per_plan(golden_cases, fake_backend):
+    """cache_matML keeps the op list of a dirty path with its plan: repeated branch moves on one edge reuse it, and the
+    cached and the first evaluation agree."""
+    from cybayes_b200 import config, likelihood
+    from cybayes_b200.driver import load_alignment
+    from cybayes_b200.mcmc_gamma import adjlist2reverse_nodes_dict, get_path2root, get_prob_t
+    from cybayes_b200.ML_gamma import cache_matML, matML
+    case = golden_cases["binary_F81"]
+    load_alignment(golden_io.data_path(case), case["dtype"], case["reader"])
+    config.MODEL, config.NORM_BETA = case["model"], case["norm_beta"]
+    tree, pi, rates, edges, site_rates = golden_io.case_state(case)
+    tmats = [get_prob_t(pi, tree, rates, r) for r in site_rates]
+    args = (config.N_SITES, config.N_TAXA, config.N_CATS)
+    lnl, cache = matML(pi, case["root"], config.LEAF_LLMAT, edges, tmats, *args)
+    path = get_path2root(adjlist2reverse_nodes_dict(tree), list(tree)[3][1], case["root"])
+    l1, _ = cache_matML(pi, case["root"], config.LEAF_LLMAT, cache, path, edges, tmats, *args)
+    plan = likelihood._plan_for(edges)
+    assert len(plan._paths) == 1
+    l2, _ = cache_matML(pi, case["root"], config.LEAF_LLMAT, cache, path, edges, tmats, *args)
+    assert len(plan._paths) == 1 and l1 == l2 == lnl
