@@ -85,8 +85,9 @@ def _spr_dirty_nodes(old_parent_of, new_tree, root):
 
 
 def run_chain(input_file, model, n_gen, thin, data_type, output_file, reader=None, seed=1234,
-              out=sys.stdout, fast_spr=False, on_generation=None):
-    """Run the chain; returns a dict with the final state, counters and timings."""
+              out=sys.stdout, fast_spr=False, on_generation=None, diag=None):
+    """Run the chain; returns a dict with the final state, counters and timings.  `diag` (a dict) receives, before
+    each on_generation call, the acceptance test's two sides: diag["ll_ratio"] and diag["log_u"]."""
     np.random.seed(seed)
     random.seed(seed)
     load_alignment(input_file, data_type, reader)
@@ -210,7 +211,10 @@ def run_chain(input_file, model, n_gen, thin, data_type, output_file, reader=Non
         current_ll = state["logLikehood"]
         ll_ratio = proposed_ll - current_ll + pr_ratio
         ll_ratio += hr
-        accepted = bool(np.log(random.random()) <= ll_ratio)
+        log_u = np.log(random.random())
+        accepted = bool(log_u <= ll_ratio)
+        if diag is not None:
+            diag["ll_ratio"], diag["log_u"] = float(ll_ratio), float(log_u)
         if accepted:
             if param == "bl":
                 state["tree"] = tree_prop

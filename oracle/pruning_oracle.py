@@ -252,14 +252,16 @@ def cache_mat_ml(pi, root, ll_mats, cache, nodes_recompute, edges, tmats, n_site
 
 
 def mat_ml_scaled(pi, root, ll_mats, edges, tmats, n_sites, n_taxa, n_cats=N_CATS, weights=None,
-                  site_lnl=False):
+                  site_lnl=False, keep=None):
     """Same recursion with per-site power-of-two rescaling (exact in fp64), so that deep
     trees do not underflow (the reference has no rescaling).  After each
     completed node every site is divided by 2**e, e = exponent of the max over
     categories and states, and e is accumulated per site.  Where the unscaled
     recursion stays in range both give the same mantissas bit for bit.
 
-    Returns (lnL, per-site lnL if asked)."""
+    Returns (lnL, per-site lnL if asked).  `keep`: dict filled with node -> (mantissas (C, S, P),
+    exponents (P,)) for the node ids it already holds as keys; every other partial is dropped as
+    soon as its parent consumed it (each node has one parent), so memory stays near the tree width."""
     C = len(tmats)
     part, expo, nkids = {}, {}, {}
     for parent, child in edges:
@@ -269,6 +271,9 @@ def mat_ml_scaled(pi, root, ll_mats, edges, tmats, n_sites, n_taxa, n_cats=N_CAT
         else:
             v = np.stack([tmats[k][parent, child].dot(part[child][k]) for k in range(C)])
             e = expo[child]
+            if keep is not None and child in keep:
+                keep[child] = (part[child], np.asarray(expo[child]))
+            del part[child], expo[child]
         if parent not in part:
             part[parent], expo[parent], nkids[parent] = v, e, 1
         else:
@@ -290,3 +295,32 @@ def mat_ml_scaled(pi, root, ll_mats, edges, tmats, n_sites, n_taxa, n_cats=N_CAT
         per_site = per_site * weights
     total = float(np.sum(per_site))
     return (total, per_site) if site_lnl else total
+
+
+def leaves_from_codes(codes, n_states, amb_sets=None):
+    """{taxon id: (S, P) 0/1 matrix} from a state-code matrix (code < S: one-hot; S + k: row k of
+    amb_sets, row 0 = all ones) -- the columns utils.pyx:94-120 would produce for those cells."""
+    amb = np.ones((1, n_states)) if amb_sets is None else np.asarray(amb_sets, dtype=float)
+    table = np.vstack([np.eye(n_states), amb])
+    return {t + 1: np.ascontiguousarray(table[codes[t].astype(np.int64)].T) for t in range(codes.shape[0])}
+
+
+def mat_ml_scaled_codes(pi, root, codes, n_states, amb_sets, edges, tmats, n_taxa, n_cats=N_CATS, chunk=16384,
+                        keep_nodes=()):
+    """mat_ml_scaled over a big state-code matrix, one chunk of columns at a time (sites are independent
+    through the whole pass, ML_gamma.pyx:24-38, so the per-site values are those of a single pass).
+    Returns (lnL, per-site lnL, {node: (mantissas (C, S, P), exponents (P,))} for keep_nodes)."""
+    n_sites = codes.shape[1]
+    per_site = np.empty(n_sites)
+    kept = {n: ([], []) for n in keep_nodes}
+    for lo in range(0, n_sites, chunk):
+        hi = min(n_sites, lo + chunk)
+        keep = {n: None for n in keep_nodes}
+        _, ps = mat_ml_scaled(pi, root, leaves_from_codes(codes[:, lo:hi], n_states, amb_sets), edges, tmats,
+                              hi - lo, n_taxa, n_cats, site_lnl=True, keep=keep)
+        per_site[lo:hi] = ps
+        for n in keep_nodes:
+            kept[n][0].append(keep[n][0])
+            kept[n][1].append(np.broadcast_to(keep[n][1], (hi - lo,)))
+    out = {n: (np.concatenate(m, axis=2), np.concatenate(e)) for n, (m, e) in kept.items()}
+    return float(np.sum(per_site)), per_site, out

@@ -198,7 +198,7 @@ def main():
         json.dump({"generator": "tests/golden/make_golden.py", "cases": cases}, fh, indent=0)
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "--nongamma"):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("--nongamma", "--c1-100k")):
     main()
 
 
@@ -226,3 +226,62 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--nongamma":
     for args in NONGAMMA:
         run_trace_nongamma(*args)
         print("trace", args[0])
+
+
+# ---- C1 at its stated length (README.md:46): narrow.phy F81, -n 100000 -t 1000 -------------------------------
+C1_MOVES = ["scale_edge", "node_slider", "rooted_NNI", "externalSPR", "mvDualSlider", "scale_alpha"]
+
+
+def run_c1_100k(n_gen=100000, thin=1000, workdir="/tmp"):
+    """Two runs of the unmodified driver on data/narrow.phy (seed 1234): the README command itself
+    (`-n 100000 -t 1000`: its .log is kept verbatim, its .trees as digest + last tree, plus the counters) and the
+    same chain with `-t 1`, from which a compact per-generation record is kept: move id and accept bit for all
+    100 000 generations, the proposed lnL of every 100th.  Existing outputs in `workdir` are reused."""
+    import numpy as np
+    runs = {}
+    for t in (thin, 1):
+        prefix = os.path.join(workdir, f"c1_t{t}")
+        if not (os.path.exists(prefix + ".log") and os.path.exists(prefix + ".stdout")):
+            cmd = [sys.executable, "mat_mcmc_gamma.code", "-i", os.path.join(REF_DATA, "narrow.phy"), "-m", "F81",
+                   "-n", str(n_gen), "-t", str(t), "-d", "bin", "-o", prefix]
+            with open(prefix + ".stdout", "w") as fh:
+                subprocess.run(cmd, cwd=REF_BUILD, stdout=fh, check=True)
+        runs[t] = prefix
+    out_dir = os.path.join(HERE, "traces")
+    # (a) the README run
+    p = runs[thin]
+    log = open(p + ".log").read()
+    trees = open(p + ".trees").read()
+    stdout = open(p + ".stdout").read().splitlines()
+    counters = [l for l in stdout if l.startswith("(np.str_(") or l.startswith("('")]
+    init = [l for l in stdout if l.startswith("Initial Likelihood")][0].split()[-1]
+    assert len(log.splitlines()) == n_gen // thin + 1
+    with open(os.path.join(out_dir, "c1_narrow_F81_100k.log"), "w") as fh:
+        fh.write(log)
+    meta = {"cmd": f"mat_mcmc_gamma.py -i data/narrow.phy -m F81 -n {n_gen} -t {thin} -d bin (seed 1234, unmodified reference)",
+            "init_lnL": init, "counters": counters, "trees_sha256": hashlib.sha256(trees.encode()).hexdigest(),
+            "last_tree": trees.strip().splitlines()[-1].split("\t")[1], "moves": C1_MOVES}
+    # (b) the same chain, every generation
+    p = runs[1]
+    gens = [l.split("\t") for l in open(p + ".stdout").read().splitlines()
+            if len(l.split("\t")) == 6 and l.split("\t")[0].isdigit()]
+    logrows = [l.split("\t") for l in open(p + ".log").read().splitlines()[1:]]
+    assert len(gens) == n_gen == len(logrows)
+    # both runs are one chain: the thinned .log rows are rows of the -t 1 .log
+    thinned = [l.split("\t") for l in log.splitlines()[1:]]
+    for row in thinned:
+        assert logrows[int(row[0]) - 1] == row, row
+    move = np.array([C1_MOVES.index(g[5]) for g in gens], dtype=np.uint8)
+    accepted = np.array([lr[1] == g[2] for g, lr in zip(gens, logrows)], dtype=bool)
+    every = 100
+    sampled = np.array([float(g[2]) for g in gens[every - 1::every]])
+    np.savez_compressed(os.path.join(out_dir, "c1_narrow_F81_100k.npz"), move=move, accepted=np.packbits(accepted),
+                        proposed_ll_every_100=sampled)
+    meta["accepted_total"] = int(accepted.sum())
+    with open(os.path.join(out_dir, "c1_narrow_F81_100k.json"), "w") as fh:
+        json.dump(meta, fh, indent=0)
+    print("c1 100k:", meta["accepted_total"], "accepted;", counters)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--c1-100k":
+    run_c1_100k()

@@ -498,3 +498,76 @@ def test_batched_nni_scoring(name, golden_cases, gpu_backend):
                 for r in site_rates]
         want = oracle.mat_ml(pi, root, ll, proposals[idx][1], tm_o, n_sites, N)[0]
         assert abs(batch[idx] - want) <= 1e-11 * abs(want), (idx, batch[idx], want)
+
+
+def _c1_golden():
+    import json
+    base = os.path.join(REPO, "tests", "golden", "traces", "c1_narrow_F81_100k")
+    meta = json.load(open(base + ".json"))
+    z = np.load(base + ".npz")
+    log = open(base + ".log").read().splitlines()
+    return meta, z["move"], np.unpackbits(z["accepted"])[:len(z["move"])].astype(bool), z["proposed_ll_every_100"], log
+
+
+def test_c1_at_its_stated_length(golden_cases, gpu_backend, tmp_path):
+    """Config C1 as the README runs it (README.md:46): narrow.phy, F81, -n 100000 -t 1000, seed 1234.  The restated
+    driver on the CUDA engine must take the recorded move and make the recorded accept/reject decision in every one
+    of the 100 000 generations (recorded from the unmodified reference, tests/golden/make_golden.py --c1-100k); on a
+    mismatch the first divergent generation and the margin |ll_ratio - log u| of its acceptance test are reported
+    (a rounding-level flip has a margin <~ 1e-9 * |lnL|)."""
+    from cybayes_b200.driver import run_chain
+    meta, move, accepted, sampled, log = _c1_golden()
+    names = meta["moves"]
+    n_gen = len(move)
+    got_move = np.empty(n_gen, dtype=np.uint8)
+    got_acc = np.empty(n_gen, dtype=bool)
+    got_ll = np.empty(n_gen)
+    margin = np.empty(n_gen)
+    diag = {}
+
+    def rec(i, cur, prop, p, mv, acc, st):
+        got_move[i - 1], got_acc[i - 1], got_ll[i - 1] = names.index(mv), acc, prop
+        margin[i - 1] = abs(diag["ll_ratio"] - diag["log_u"])
+    res = run_chain(golden_io.data_path(golden_cases["narrow_F81"]), "F81", n_gen, 1000, "bin", str(tmp_path / "c1"),
+                    out=io.StringIO(), on_generation=rec, diag=diag)
+    bad = np.nonzero((got_move != move) | (got_acc != accepted))[0]
+    if bad.size:
+        g = int(bad[0])
+        pytest.fail(f"first divergent generation {g + 1}: move {names[got_move[g]]} (reference {names[move[g]]}), "
+                    f"accepted {bool(got_acc[g])} (reference {bool(accepted[g])}), proposed lnL {got_ll[g]!r}, "
+                    f"margin |ll_ratio - log u| = {margin[g]:.3e}")
+    np.testing.assert_allclose(got_ll[99::100], sampled, rtol=REL_CLOSED, atol=0)
+    # the .log of the README command: tree length and alpha exact strings, lnL to 1e-11; final tree and counters exact
+    rows = open(str(tmp_path / "c1.log")).read().splitlines()
+    assert len(rows) == len(log) and rows[0] == log[0]
+    for r, g in zip(rows[1:], log[1:]):
+        r, g = r.split("\t"), g.split("\t")
+        assert (r[0], r[2], r[3]) == (g[0], g[2], g[3]), (r, g)
+        assert abs(float(r[1]) - float(g[1])) <= REL_CLOSED * abs(float(g[1])), (r, g)
+    trees = open(str(tmp_path / "c1.trees")).read()
+    assert trees.strip().splitlines()[-1].split("\t")[1] == meta["last_tree"]
+    import hashlib
+    assert hashlib.sha256(trees.encode()).hexdigest() == meta["trees_sha256"]
+    counters = sorted(f"({str(k[0])!r}, {k[1]!r}) {res['accepts'].get(k, 0)} {v}" for k, v in res["moves"].items())
+    assert counters == sorted(c.replace("np.str_(", "").replace("'),", "',", 1) for c in meta["counters"])
+    print(f"C1 100k: smallest acceptance margin over the run {margin.min():.3e} at generation {int(margin.argmin()) + 1}")
+
+
+def test_c1_at_its_stated_length_unmodified_script(gpu_backend, tmp_path, monkeypatch, capsys):
+    """The same README command through the reference's own, unmodified driver script on the compat modules: its
+    .log (TL, alpha exact; lnL 1e-11), its .trees (byte-exact, by digest) and its counters equal the recorded run."""
+    import hashlib
+    from conftest import run_reference_script
+    meta, _, _, _, log = _c1_golden()
+    out = run_reference_script("mat_mcmc_gamma", ["-i", os.path.join(REPO, "tests", "golden", "data", "narrow.phy"),
+                                                  "-m", "F81", "-n", "100000", "-t", "1000", "-d", "bin", "-o",
+                                                  str(tmp_path / "c1ref")], monkeypatch, capsys)
+    rows = open(str(tmp_path / "c1ref.log")).read().splitlines()
+    assert len(rows) == len(log)
+    for r, g in zip(rows[1:], log[1:]):
+        r, g = r.split("\t"), g.split("\t")
+        assert (r[0], r[2], r[3]) == (g[0], g[2], g[3]), (r, g)
+        assert abs(float(r[1]) - float(g[1])) <= REL_CLOSED * abs(float(g[1])), (r, g)
+    assert hashlib.sha256(open(str(tmp_path / "c1ref.trees")).read().encode()).hexdigest() == meta["trees_sha256"]
+    counters = [l for l in out.splitlines() if l.startswith("(np.str_(") or l.startswith("('")]
+    assert sorted(counters) == sorted(meta["counters"])

@@ -330,3 +330,14 @@ def test_dirty_path_op_lists_are_cached_per_plan(golden_cases, fake_backend):
     assert len(plan._paths) == 1
     l2, _ = cache_matML(pi, case["root"], config.LEAF_LLMAT, cache, path, edges, tmats, *args)
     assert len(plan._paths) == 1 and l1 == l2 == lnl
+
+
+def test_large_shape_parity_bodies_dry_run(fake_backend, monkeypatch):
+    """The bodies of the benchmark-shape GPU parity tests (tests/large_cases.py), run small on the oracle-backed fake
+    engine: keeps the test logic itself (kept partials, dirty-path bookkeeping, slot tables) exercised on CPU."""
+    import large_cases
+    from cybayes_b200 import likelihood
+    monkeypatch.setattr(likelihood, "COMPRESS_MAX_SITES", 0)
+    large_cases.run_c4_shape(48, 512, 128)
+    likelihood.reset_engines()
+    large_cases.run_c5_shape(12, 256, 64, 128)
