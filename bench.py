@@ -1,14 +1,15 @@
 #!/usr/bin/env python3
-"""Benchmark of the tree-likelihood hot path (contract in the task statement / DESIGN.md).
+"""Benchmark of the tree-likelihood hot path (contract in the task statement / DESIGN.md section 5).
 
-  python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA engine)
-  python bench.py --impl reference [...]                      the reference's own CPU path
+  python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA engine), config C4
+  python bench.py --impl reference [...]                      the reference's own CPU path, same config
+  python bench.py --config C5|C1|C2|C3 [...]                  the other BASELINE.json configurations, same schema
 
-Workload (BASELINE.json, config C4): synthetic 1024 taxa x 1,000,000 binary site patterns,
-GTR + discrete-Gamma-4, one *step* = one full Felsenstein pruning pass (log-likelihood
-evaluation) keeping the partial cache.  For N > 1 the patterns are sharded over the ranks (one
-process per GPU, torchrun), each rank runs the same op list on its slice and the only exchange is
-the scalar NCCL all-reduce inside the library: strong scaling, `value` = whole-alignment evals/s.
+Workload at the defaults (BASELINE.json, config C4): synthetic 1024 taxa x 1,000,000 binary site patterns,
+GTR + discrete-Gamma-4, one *step* = one full Felsenstein pruning pass (log-likelihood evaluation) keeping the
+partial cache.  For N > 1 the patterns are sharded over the ranks (one process per GPU, torchrun), each rank runs
+the same op list on its slice and the only exchange is the scalar NCCL all-reduce inside the library: strong
+scaling, `value` = whole-alignment evals/s.
 
 One JSON line is printed by rank 0.
 """
@@ -31,6 +32,12 @@ SEED = 20260101
 BLOCK = 125000          # generation / sharding granule: 1M = 8 blocks
 METRIC = "tree log-likelihood evals/sec"
 UNIT = "evals/s"
+DATA = os.path.join(REPO, "tests", "golden", "data")
+REAL = {   # BASELINE.json configs[0..2]
+    "C1": ("narrow.phy", "readBinaryPhy", "bin", "F81"),
+    "C2": ("IELex-2016.prog.phy", "readPhy", "multi", "JC"),
+    "C3": ("ielex_multistate.phy", "readPhy", "multi", "F81"),
+}
 
 
 def parse():
@@ -39,20 +46,38 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--taxa", type=int, default=1024)
-    ap.add_argument("--patterns", type=int, default=1000000)
-    ap.add_argument("--sample-sites", type=int, default=20000, help="sites of the cpu_baseline sample")
-    ap.add_argument("--ref-chunk", type=int, default=10000, help="sites per worker of --impl reference")
+    ap.add_argument("--config", default="C4", choices=["C4", "C5", "C1", "C2", "C3"])
+    ap.add_argument("--taxa", type=int, default=None)
+    ap.add_argument("--patterns", type=int, default=None)
+    ap.add_argument("--ref-chunk", type=int, default=10000, help="sites per matML call of --impl reference")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / dirty-path / MCMC extras")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.taxa is None:
+        a.taxa = 512 if a.config == "C5" else 1024
+    if a.patterns is None:
+        a.patterns = 200000 if a.config == "C5" else 1000000
+    a.warmup = max(a.warmup, 3)
+    return a
 
 
 def workload_name(a):
+    if a.config == "C5":
+        return (f"C5: synthetic {a.taxa} taxa x {a.patterns} site patterns x 64 states, GTR + Gamma-4, full pruning "
+                "pass (likelihood evaluation)")
     return (f"C4: synthetic {a.taxa} taxa x {a.patterns} binary site patterns, GTR + Gamma-4, "
             "full pruning pass (likelihood evaluation) with the partial cache kept")
 
 
-def measured_peak():
+def config_dict(a):
+    """The same dict for both arms (`--impl ours` / `--impl reference`)."""
+    S = 64 if a.config == "C5" else 2
+    per_gpu = -(-a.patterns // a.gpus)
+    return {"workload": workload_name(a), "n_taxa": a.taxa, "n_patterns": a.patterns, "n_states": S, "n_cats": 4,
+            "model": "GTR", "parallelism": f"site-sharded x{a.gpus}", "patterns_per_gpu": per_gpu,
+            "l2": "inputs per step (GBs of partials per GPU) are far larger than the 126 MB L2; no flush"}
+
+
+def measured_peaks():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as fh:
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -90,59 +115,65 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 # ------------------------------------------------------------------------------------ reference arm
-_REF = {}
+def reference_available():
+    d = os.path.join(REPO, "oracle", "_ref")
+    return os.path.exists(d) and any(f.startswith("ML_gamma") and f.endswith(".so") for f in os.listdir(d))
 
 
-def _ref_worker_init(taxa, patterns, chunk, counter):
-    """Runs in a spawned process: import the compiled, unmodified reference; when `counter` is given,
-    take the next block index and prepare that chunk of the alignment."""
+def _ref_setup(taxa, patterns, n_states, seed, chunk):
+    """In a worker process: import the compiled, unmodified reference (oracle/_ref/*.so) and describe the alignment."""
     import random
     sys.path.insert(0, os.path.join(REPO, "oracle", "_ref"))
-    import config as rconfig      # the reference's modules (oracle/_ref/*.so)
+    import config as rconfig
     import mcmc_gamma as rmcmc
     import ML_gamma as rml
     from cybayes_b200.synthetic import SyntheticAlignment
-    aln = SyntheticAlignment(taxa, patterns, 2, SEED, block_sites=chunk)
-    _REF.update(aln=aln, rml=rml, rconfig=rconfig, rmcmc=rmcmc, chunk=chunk)
+    aln = SyntheticAlignment(taxa, patterns, n_states, seed, block_sites=chunk)
     random.seed(1)
-    if counter is not None:
-        with counter.get_lock():
-            idx = counter.value
-            counter.value += 1
-        _ref_prepare(idx % max(1, patterns // chunk))
-
-
-def _ref_prepare(block_index):
-    aln, rconfig, rmcmc = _REF["aln"], _REF["rconfig"], _REF["rmcmc"]
-    codes = aln.codes(block_index * _REF["chunk"], (block_index + 1) * _REF["chunk"])
-    eye = np.eye(2)
-    rconfig.N_TAXA, rconfig.N_CHARS, rconfig.N_SITES = aln.n_taxa, 2, codes.shape[1]
-    rconfig.MODEL, rconfig.IN_DTYPE = "GTR", "bin"
-    _REF["leaves"] = {t + 1: np.ascontiguousarray(eye[codes[t]].T) for t in range(aln.n_taxa)}
+    rconfig.N_TAXA, rconfig.N_CHARS = taxa, n_states
+    rconfig.MODEL, rconfig.IN_DTYPE = "GTR", ("bin" if n_states == 2 else "multi")
     pi, er = aln.pi.copy(), aln.er.copy()
-    _REF["tmats"] = [rmcmc.get_prob_t(pi, aln.tree, er, r) for r in aln.rates]
-    _REF["edges"] = aln.edge_order()
-    _REF["pi"] = pi
-    return codes.shape[1]
+    tmats = [rmcmc.get_prob_t(pi, aln.tree, er, r) for r in aln.rates]   # the reference's own P(t) (scipy expm)
+    return aln, rconfig, rml, tmats, pi
 
 
-def _ref_eval(_):
-    aln = _REF["aln"]
-    t0 = time.perf_counter()
-    lnl, _cache = _REF["rml"].matML(_REF["pi"], aln.root, _REF["leaves"], _REF["edges"], _REF["tmats"],
-                                    _REF["rconfig"].N_SITES, aln.n_taxa, 4)
-    return time.perf_counter() - t0, float(lnl)
+def _ref_leaves(codes, n_states):
+    eye = np.eye(n_states)
+    return {t + 1: np.ascontiguousarray(eye[codes[t]].T) for t in range(codes.shape[0])}
 
 
-def reference_available():
-    return os.path.exists(os.path.join(REPO, "oracle", "_ref")) and any(
-        f.startswith("ML_gamma") and f.endswith(".so") for f in os.listdir(os.path.join(REPO, "oracle", "_ref")))
+def _ref_worker(rank, n_workers, taxa, patterns, n_states, seed, chunk, chunk_ids, n_rounds, barrier, out):
+    """One host core of the reference arm: prepares its chunks of the alignment once, then on every barrier
+    evaluates all of them with the reference's ML_gamma.matML (ML_gamma.pyx:7-42)."""
+    aln, rconfig, rml, tmats, pi = _ref_setup(taxa, patterns, n_states, seed, chunk)
+    edges = aln.edge_order()
+    mine = []
+    for b in chunk_ids:
+        codes = aln.codes(b * chunk, min(patterns, (b + 1) * chunk))
+        mine.append((_ref_leaves(codes, n_states), codes.shape[1]))
+    barrier.wait()                       # everybody is prepared
+    for _ in range(n_rounds):
+        barrier.wait()                   # start of a step
+        total = 0.0
+        for leaves, n in mine:
+            rconfig.N_SITES = n
+            lnl, _cache = rml.matML(pi, aln.root, leaves, edges, tmats, n, taxa, 4)
+            total += float(lnl)
+        out[rank] = total
+        barrier.wait()                   # end of a step
 
 
 def run_reference_arm(a):
-    """The reference's own Cython + NumPy matML on every host core (independent site chunks; the
-    reference itself is single-threaded by construction, utils.pyx:3-7)."""
+    """The reference's own Cython + NumPy matML on every host core.  The reference is single-threaded by
+    construction (utils.pyx:3-7) and cannot hold the cache of the full alignment (65 GB at C4), so the alignment is
+    cut into site chunks (sites are independent, so the sum of the chunk evaluations IS the reference's evaluation,
+    BASELINE.md plan step 3) that are spread over the cores; a step evaluates EVERY chunk once -- the whole
+    workload is timed, nothing is extrapolated (unless host memory is too small, which is then stated)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -150,69 +181,109 @@ def run_reference_arm(a):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (oracle/build_ref.sh)"}))
         return
     import multiprocessing as mp
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    try:  # each worker holds ~0.2 GB of leaves and produces a ~0.7 GB cache per call
+    S = 64 if a.config == "C5" else 2
+    seed = 20260102 if a.config == "C5" else SEED
+    chunk = min(a.ref_chunk if a.config != "C5" else 500, a.patterns)
+    n_chunks = -(-a.patterns // chunk)
+    cores = min(host_cores(), n_chunks)
+    leaf_bytes = a.taxa * S * chunk * 8
+    cache_bytes = (a.taxa - 1) * 4 * S * chunk * 8
+    sampled = False
+    try:
         import psutil
-        cores = max(1, min(cores, int(psutil.virtual_memory().available / 1.5e9)))
+        avail = psutil.virtual_memory().available
     except Exception:
-        pass
+        avail = 64e9
+    ids = list(range(n_chunks))
+    # C5 at full size costs ~150 core-seconds per evaluation: bound the step to a sample there (stated below)
+    budget_chunks = n_chunks
+    if a.config == "C5":
+        budget_chunks = min(n_chunks, cores * 2)
+    if n_chunks * leaf_bytes + cores * (cache_bytes + leaf_bytes) * 1.5 > 0.8 * avail:
+        budget_chunks = min(budget_chunks, cores)
+    if budget_chunks < n_chunks:
+        ids, sampled = ids[:budget_chunks], True
+    per_worker = [ids[w::cores] for w in range(cores)]
     ctx = mp.get_context("spawn")
-    counter = ctx.Value("i", 0)
-    with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(a.taxa, a.patterns, a.ref_chunk, counter)) as pool:
-        for _ in range(a.warmup):
-            pool.map(_ref_eval, range(cores), chunksize=1)
+    barrier = ctx.Barrier(cores + 1)
+    out = ctx.Array("d", cores)
+    n_rounds = a.warmup + a.steps
+    procs = [ctx.Process(target=_ref_worker, args=(w, cores, a.taxa, a.patterns, S, seed, chunk, per_worker[w], n_rounds,
+                                                   barrier, out)) for w in range(cores)]
+    for p in procs:
+        p.start()
+    barrier.wait()
+    times, lnl = [], None
+    for r in range(n_rounds):
+        barrier.wait()
         t0 = time.perf_counter()
-        for _ in range(a.steps):
-            pool.map(_ref_eval, range(cores), chunksize=1)
-        dt = (time.perf_counter() - t0) / a.steps
-    sites_per_s = cores * a.ref_chunk / dt
-    value = sites_per_s / a.patterns
-    sample = (f"{cores} processes x {a.ref_chunk} sites of the same synthetic alignment per step; evals/s of the full "
-              f"{a.patterns}-site alignment extrapolated linearly (sites are independent)")
+        barrier.wait()
+        if r >= a.warmup:
+            times.append(time.perf_counter() - t0)
+        lnl = sum(out[:])
+    for p in procs:
+        p.join()
+    dt = sum(times) / len(times)
+    sites = sum(min(chunk, a.patterns - b * chunk) for b in ids)
+    value = sites / dt / a.patterns
+    if sampled:
+        sample = (f"{len(ids)} of {n_chunks} chunks of {chunk} sites on {cores} processes per step ({sites} sites); "
+                  f"evals/s of the full {a.patterns}-site alignment extrapolated linearly (sites are independent)")
+    else:
+        sample = (f"the whole alignment every step: {n_chunks} chunks of {chunk} sites spread over {cores} "
+                  "single-threaded processes, nothing extrapolated")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "n_taxa": a.taxa, "n_patterns": a.patterns, "n_states": 2,
-                   "n_cats": 4, "model": "GTR"},
+        "warmup": a.warmup, "ms_per_step": dt * 1e3 * (a.patterns / sites), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(a),
+        "lnL": lnl if not sampled else None, "lnL_sites": sites,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def cpu_baseline_sample(a, codes_sample):
-    """1-core reference matML on the first `sample-sites` columns of OUR data (spawned process so
-    the reference's top-level modules never meet the product's).  Returns (dict, lnL of sample)."""
+def _cpu_baseline_child(taxa, patterns, n_states, seed, chunk, block_index, reps, conn):
+    """1 core, spawned so the reference's top-level modules never meet the product's: matML on one chunk."""
+    aln, rconfig, rml, tmats, pi = _ref_setup(taxa, patterns, n_states, seed, chunk)
+    codes = aln.codes(block_index * chunk, min(patterns, (block_index + 1) * chunk))
+    leaves = _ref_leaves(codes, n_states)
+    edges = aln.edge_order()
+    rconfig.N_SITES = codes.shape[1]
+    secs, lnl = [], None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        lnl, _cache = rml.matML(pi, aln.root, leaves, edges, tmats, codes.shape[1], taxa, 4)
+        secs.append(time.perf_counter() - t0)
+        del _cache
+    ekeys = list(aln.tree.keys())
+    mats = np.stack([np.asarray(tmats[k][e]) for k in range(4) for e in ekeys])
+    conn.send((secs, float(lnl), mats))
+    conn.close()
+
+
+def cpu_baseline_chunk(a, n_states, seed, chunk, reps=2):
+    """The compiled reference on ONE core on chunk 0 of the same alignment.  Returns (dict, lnL of the chunk, the
+    reference's own P matrices) -- the GPU is then checked on exactly that chunk with exactly those matrices."""
     if not reference_available():
         return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference",
-                "sample": "unavailable: oracle/_ref not built"}, None
+                "sample": "unavailable: oracle/_ref not built"}, None, None
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
-    with ctx.Pool(1, initializer=_ref_sample_init, initargs=(a.taxa, a.patterns, codes_sample)) as pool:
-        pool.map(_ref_eval, [0])
-        res = pool.map(_ref_eval, [0, 1, 2], chunksize=1)
-    sec = statistics.median(r[0] for r in res)
-    n = codes_sample.shape[1]
+    parent, child = ctx.Pipe()
+    p = ctx.Process(target=_cpu_baseline_child, args=(a.taxa, a.patterns, n_states, seed, chunk, 0, reps, child))
+    p.start()
+    secs, lnl, mats = parent.recv()
+    p.join()
+    sec = min(secs)
+    n = min(chunk, a.patterns)
     return {"value": 1.0 / (sec * a.patterns / n), "unit": UNIT, "cores": 1, "kind": "reference",
-            "sample": f"first {n} of {a.patterns} sites, median of 3 matML calls ({sec:.3f} s each), extrapolated "
-                      "linearly in the site count (sites are independent)"}, res[0][1]
-
-
-def _ref_sample_init(taxa, patterns, codes_sample):
-    _ref_worker_init(taxa, patterns, BLOCK, None)
-    aln, rconfig, rmcmc = _REF["aln"], _REF["rconfig"], _REF["rmcmc"]
-    eye = np.eye(2)
-    rconfig.N_TAXA, rconfig.N_CHARS, rconfig.N_SITES = taxa, 2, codes_sample.shape[1]
-    rconfig.MODEL, rconfig.IN_DTYPE = "GTR", "bin"
-    _REF["leaves"] = {t + 1: np.ascontiguousarray(eye[codes_sample[t]].T) for t in range(taxa)}
-    pi, er = aln.pi.copy(), aln.er.copy()
-    _REF["tmats"] = [rmcmc.get_prob_t(pi, aln.tree, er, r) for r in aln.rates]
-    _REF["edges"] = aln.edge_order()
-    _REF["pi"] = pi
+            "sample": f"sites [0, {n}) of {a.patterns}: best of {reps} ML_gamma.matML calls of the compiled reference "
+                      f"({sec:.2f} s each), evals/s of the full alignment = linear in the site count (sites are "
+                      "independent)"}, lnl, mats
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def run_ours(a):
+def _rendezvous(a):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -222,14 +293,42 @@ def run_ours(a):
     if world > 1:
         import torch.distributed as dist  # host-side rendezvous only (gloo); no torch on the device path
         dist.init_process_group("gloo")
+    os.environ["CYBAYES_DEVICE"] = str(local)
+    return rank, world, local, dist
 
-    from cybayes_b200 import _lib, config, likelihood
+
+def _max_over_ranks(dist, *vals):
+    if dist is None:
+        return vals if len(vals) > 1 else vals[0]
+    import torch
+    t = torch.tensor(list(vals), dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = [float(x) for x in t]
+    return out if len(out) > 1 else out[0]
+
+
+def _tables(eng, aln, plan, C):
+    """K1: every P(t r) of the tree in one launch; returns (slots, pslots table of the plan, slot_of, ekeys, d)."""
+    from cybayes_b200 import _lib
+    from cybayes_b200.subst import gtr_eigensystem
+    ekeys = list(aln.tree.keys())
+    n_e = len(ekeys)
+    block = eng.alloc_slots(n_e * C)
+    slots = np.arange(block.base, block.base + n_e * C, dtype=np.int32)
+    d = np.array([aln.tree[e] * r for r in aln.rates for e in ekeys])
+    eng.queue_build(_lib.CB_MODEL_GTR_EIG, aln.pi, 0.0, gtr_eigensystem(aln.pi, aln.er), slots, d)
+    slot_of = {(k, e): block.base + k * n_e + i for k in range(C) for i, e in enumerate(ekeys)}
+    pslots = np.array([[slot_of[k, e] for k in range(C)] for e in plan.edge_keys], dtype=np.int32)
+    return block, slots, pslots, slot_of, ekeys
+
+
+def run_c4(a):
+    rank, world, local, dist = _rendezvous(a)
+    from cybayes_b200 import config, likelihood
     from cybayes_b200.alignment import LeafMatrices
     from cybayes_b200.ML_gamma import matML
-    from cybayes_b200.subst import gtr_eigensystem
     from cybayes_b200.synthetic import SyntheticAlignment, shard_bounds
 
-    os.environ["CYBAYES_DEVICE"] = str(local)
     aln = SyntheticAlignment(a.taxa, a.patterns, 2, SEED, block_sites=BLOCK)
     lo, hi = shard_bounds(a.patterns, rank, world, BLOCK)
     t_gen = time.perf_counter()
@@ -249,14 +348,8 @@ def run_ours(a):
 
     edges = aln.edge_order()
     plan = likelihood._plan_for(edges)
-    ekeys = list(aln.tree.keys())
+    block, slots, pslots, slot_of, ekeys = _tables(eng, aln, plan, C)
     n_e = len(ekeys)
-    block = eng.alloc_slots(n_e * C)
-    slots = np.arange(block.base, block.base + n_e * C, dtype=np.int32)
-    d = np.array([aln.tree[e] * r for r in aln.rates for e in ekeys])
-    eng.queue_build(_lib.CB_MODEL_GTR_EIG, aln.pi, 0.0, gtr_eigensystem(aln.pi, aln.er), slots, d)  # K1: one launch
-    slot_of = {(k, e): block.base + k * n_e + i for k in range(C) for i, e in enumerate(ekeys)}
-    pslots = np.array([[slot_of[k, e] for k in range(C)] for e in plan.edge_keys], dtype=np.int32)
     pi = aln.pi
 
     def step():
@@ -274,59 +367,61 @@ def run_ours(a):
     eng.sync()
     clocks = ClockSampler(local) if rank == 0 else None
     st0 = eng.stats()
-    kernel_ms = []
+    kernel_ms, main_ms = [], []
     eng.mark(0)
     t0 = time.perf_counter()
     for _ in range(a.steps):
         lnl = step()
         kernel_ms.append(eng.last_eval_ms())
+        main_ms.append(eng.last_eval_main_ms())
     eng.mark(1)
     eng.sync()
     wall = time.perf_counter() - t0
     dev_ms = eng.mark_elapsed_ms()
     st1 = eng.stats()
+    info = eng.last_eval_info()
     barrier()
     clock_rec = clocks.stop() if clocks else None
-    if dist is not None:
-        import torch
-        t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms = float(t[0]), float(t[1])
-    else:
-        wall_ms = wall * 1e3
+    dev_ms, wall_ms = _max_over_ranks(dist, dev_ms, wall * 1e3)
     ms_per_step = dev_ms / a.steps
     value = 1e3 / ms_per_step
 
-    # roofline of the dominant kernel (prune_s2_kernel<4>): algorithmic bytes of THIS rank's shard per
-    # evaluation / device time of the evaluation's launches (CUDA events on the launching stream)
-    alg_bytes = 16.0 * C * S * n_local * (N - 2) + 1.0 * N * n_local + 8.0 * n_local
-    k_ms = statistics.mean(kernel_ms)
-    peak, peak_src = measured_peak()
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    # Roofline of the dominant kernel (the pruning launch; prune_s2t_kernel<4> from 75 776 patterns per GPU):
+    # bytes this evaluation HAS to move, from its op list (stored partials + exponents written once; stored partials
+    # read back, tip codes and pattern weights read once; children carried in registers / the shared-memory stack and
+    # folded cherries move nothing) / the launch's device time (CUDA events on the launching stream) / measured copy peak.
+    k_ms = statistics.mean(main_ms)
+    peak, peak_src = measured_peaks()
+    required = info["bytes_written"] + info["bytes_read"]
+    achieved = required / (k_ms * 1e-3) / 1e9
+    alg_bytes = 16.0 * C * S * n_local * (N - 2) + 1.0 * N * n_local + 8.0 * n_local   # every partial written AND read
     traffic = None
     try:
         with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as fh:
-            traffic = json.load(fh).get("prune_s2_kernel_dram_bytes_per_eval_1M")
-            if traffic is not None and (a.patterns != 1000000 or world != 1):
-                traffic = None
+            tj = json.load(fh)
+            if a.patterns == 1000000 and world == 1 and a.taxa == 1024:
+                traffic = tj.get("prune_s2t_kernel_dram_bytes_per_eval_1M")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "prune_s2_kernel<4>", "algorithmic_bytes_per_eval": alg_bytes,
-                "kernel_ms_per_eval": k_ms, "peak_source": peak_src,
-                "launches_per_eval": (st1["kernel_launches"] - st0["kernel_launches"]) / a.steps}
-    if traffic is not None:
-        # the walk never writes carried / folded partials, so it moves fewer bytes than the algorithmic count: the
-        # bandwidth it actually draws (ncu DRAM bytes of this kernel / this run's kernel time) against the same peak
-        roofline["traffic_GBps"] = traffic / (k_ms * 1e-3) / 1e9
-        roofline["traffic_frac"] = roofline["traffic_GBps"] / peak
+                "traffic": traffic, "kernel": "prune_s2t_kernel<4>" if n_local >= 75776 else "prune_s2_kernel<4>",
+                "required_bytes_per_eval": required, "bytes_written": info["bytes_written"],
+                "bytes_read": info["bytes_read"], "kernel_ms_per_eval": k_ms,
+                "eval_ms_incl_prepass": statistics.mean(kernel_ms), "peak_source": peak_src,
+                "launches_per_eval": (st1["kernel_launches"] - st0["kernel_launches"]) / a.steps,
+                "op_list": {k: info[k] for k in ("ops", "stored", "read_back", "stack_pops", "spills", "cherries_folded",
+                                                 "launches")},
+                "survey_8d": {"algorithmic_bytes_per_eval": alg_bytes, "GBps": alg_bytes / (k_ms * 1e-3) / 1e9,
+                              "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak,
+                              "note": "SURVEY 8(d) counts every non-root partial as written and read back; the walk "
+                                      "carries / stacks / folds most of them, so this ratio is not a bandwidth fraction"}}
 
     # end to end through the reference-facing call: host P matrices (numpy, one dict per category) ->
     # matML -> float.  Timed region holds the H2D of P matrices + op descriptors and the D2H of lnL.
     host_p = eng.download_pmats(slots).reshape(C, n_e, S, S)
     tm_host = [{e: host_p[k, i] for i, e in enumerate(ekeys)} for k in range(C)]
     args = (n_local, N, C)
-    for _ in range(2):
+    for _ in range(3):
         l2, cache = matML(pi, aln.root, leaves, edges, tm_host, *args)
         del cache
     barrier()
@@ -338,11 +433,7 @@ def run_ours(a):
         del cache
     e2e_s = (time.perf_counter() - t0) / a.steps
     s1 = eng.stats()
-    if dist is not None:
-        import torch
-        t = torch.tensor([e2e_s], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
+    e2e_s = _max_over_ranks(dist, e2e_s)
     assert abs(l2 - lnl) <= 1e-12 * abs(lnl), (l2, lnl)
     e2e = {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) / a.steps,
            "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) / a.steps,
@@ -351,10 +442,9 @@ def run_ours(a):
 
     # The same call fed the way this package's own drop-in modules feed it: get_prob_t_all builds the tables on the
     # device from (pi, rates, branch lengths), matML takes the device tables -- what the unchanged reference driver
-    # does on the compat modules.  Per step: a few KB of scalars + the op list in, lnL out.  Reported next to `e2e`
-    # (which keeps the reference-style HOST matrices as its input), not instead of it.
+    # does on the compat modules.  Reported next to `e2e` (which keeps reference-style HOST matrices as its input).
     from cybayes_b200.subst import get_prob_t_all
-    for _ in range(2):
+    for _ in range(3):
         tabs = get_prob_t_all(pi, aln.tree, aln.er, aln.rates)
         l3, cache = matML(pi, aln.root, leaves, edges, tabs, *args)
         del cache, tabs
@@ -368,11 +458,7 @@ def run_ours(a):
         del cache, tabs
     dev_s = (time.perf_counter() - t0) / a.steps
     s1 = eng.stats()
-    if dist is not None:
-        import torch
-        t = torch.tensor([dev_s], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s = float(t[0])
+    dev_s = _max_over_ranks(dist, dev_s)
     assert abs(l3 - lnl) <= 1e-9 * abs(lnl), (l3, lnl)
     e2e["device_built_tables"] = {"value": 1.0 / dev_s, "unit": UNIT,
                                   "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) / a.steps,
@@ -382,11 +468,9 @@ def run_ours(a):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "n_taxa": N, "n_patterns": a.patterns, "n_states": S, "n_cats": C,
-                   "model": "GTR", "patterns_per_gpu": n_local, "parallelism": f"site-sharded x{world}",
-                   "l2": "inputs per step (>= 8 GB of partials per GPU) are far larger than the 126 MB L2; no flush"},
-        "lnL": lnl, "wall_ms_per_step": wall_ms / a.steps, "roofline": roofline, "e2e": e2e,
+        "dtype": "f64", "data": "synthetic", "config": config_dict(a),
+        "lnL": lnl, "wall_ms_per_step": wall_ms / a.steps, "host_ms_per_step": ms_per_step - statistics.mean(kernel_ms),
+        "roofline": roofline, "e2e": e2e,
         "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"], "clocks": clock_rec,
         "data_generation_s": t_gen,
     }
@@ -407,44 +491,57 @@ def run_ours(a):
             ch = np.array([c for n in path for c in plan.kids[n]], dtype=np.int32)
             ps = np.array([[slot_of[k, (n, c)] for k in range(C)] for n in path for c in plan.kids[n]], dtype=np.int32)
             paths.append((nodes, ch, ps))
-        if world == 1:
-            ms = []
-            for nodes, ch, ps in paths:
-                l_d, s2 = eng.eval(snap, nodes, ch, ps, pi, want_snapshot=True)
-                ms.append(eng.last_eval_ms())
-                eng.release_snapshot(s2)
-                assert l_d == l_full
-            mean_len = statistics.mean(len(p[0]) for p in paths)
-            out["dirty_path"] = {"evals_per_sec": 1e3 / statistics.mean(ms[2:]), "mean_path_nodes": mean_len,
-                                 "kernel_ms": statistics.mean(ms[2:]), "launches_per_eval": 1,
-                                 "check": "each equals the full-pass lnL bit for bit"}
+        ms, req = [], []
+        for nodes, ch, ps in paths:
+            l_d, s2 = eng.eval(snap, nodes, ch, ps, pi, want_snapshot=True)
+            ms.append(eng.last_eval_main_ms())
+            i2 = eng.last_eval_info()
+            req.append(i2["bytes_written"] + i2["bytes_read"])
+            eng.release_snapshot(s2)
+            assert l_d == l_full
+        mean_len = statistics.mean(len(p[0]) for p in paths)
+        d_ms, d_req = statistics.mean(ms[2:]), statistics.mean(req[2:])
+        out["dirty_path"] = {"evals_per_sec": 1e3 / d_ms, "mean_path_nodes": mean_len, "kernel_ms": d_ms,
+                             "launches_per_eval": 2 if n_local >= 75776 else 1,
+                             "roofline": {"bound": "hbm", "required_bytes_per_eval": d_req,
+                                          "achieved": d_req / (d_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                          "frac": d_req / (d_ms * 1e-3) / 1e9 / peak},
+                             "check": "each equals the full-pass lnL bit for bit"}
         eng.release_snapshot(snap)
         # likelihood only (no cache kept): what a proposal that is going to be rejected costs
         ms = []
         for _ in range(6):
             l_only, _ = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=False)
-            ms.append(eng.last_eval_ms())
+            ms.append(eng.last_eval_main_ms())
         assert l_only == l_full
+        i3 = eng.last_eval_info()
         out["lnl_only"] = {"evals_per_sec": 1e3 / statistics.mean(ms[2:]), "kernel_ms": statistics.mean(ms[2:]),
-                           "note": "same walk, only the partials that must be read back are written"}
+                           "required_bytes_per_eval": i3["bytes_written"] + i3["bytes_read"],
+                           "note": "same walk, nothing stored except the partials the walk itself re-reads"}
 
     if rank == 0 and world == 1 and not a.no_extras:
-        # CPU baseline beside it: the compiled reference, 1 core, on a bounded sample of the same data,
-        # and a parity check of the GPU path against it on that sample.
-        ns = min(a.sample_sites, n_local)
-        sample = np.ascontiguousarray(codes[:, :ns])
-        base, ref_lnl = cpu_baseline_sample(a, sample)
+        # CPU baseline beside it: the compiled reference, 1 core, on one 125 000-site chunk of the same data -- and the
+        # parity check of BASELINE.md plan step 4: that chunk through the SAME kernel instantiation (>= 75 776
+        # patterns) with the reference's own P matrices, single-launch walk and split walk.
+        chunk = min(BLOCK, n_local)
+        base, ref_lnl, ref_mats = cpu_baseline_chunk(a, S, SEED, chunk)
         out["cpu_baseline"] = base
         if ref_lnl is not None:
             from cybayes_b200.engine import Engine
-            e2 = Engine(sample, S, C, device=local)
+            e2 = Engine(np.ascontiguousarray(codes[:, :chunk]), S, C, device=local)
             b2 = e2.alloc_slots(n_e * C)
-            sl2 = np.arange(b2.base, b2.base + n_e * C, dtype=np.int32)
-            e2.queue_build(_lib.CB_MODEL_GTR_EIG, aln.pi, 0.0, gtr_eigensystem(aln.pi, aln.er), sl2, d)
-            got, _ = e2.eval(None, plan.nodes, plan.children, pslots - block.base + b2.base, pi, want_snapshot=False)
+            e2.upload_pmats(np.arange(b2.base, b2.base + n_e * C, dtype=np.int32), ref_mats)
+            ps2 = pslots - block.base + b2.base
+            got_walk, _ = e2.eval(None, plan.nodes, plan.children, ps2, pi, want_snapshot=False, force_walk=True)
+            got_split, sn = e2.eval(None, plan.nodes, plan.children, ps2, pi, want_snapshot=True)
+            launches = e2.last_eval_info()["launches"]
             e2.close()
-            out["cpu_baseline"]["parity"] = {"sample_lnL_reference": ref_lnl, "sample_lnL_gpu": got,
-                                             "rel_err": abs(got - ref_lnl) / abs(ref_lnl)}
+            out["cpu_baseline"]["parity"] = {
+                "chunk_sites": chunk, "chunk_lnL_reference": ref_lnl, "chunk_lnL_gpu_single_walk": got_walk,
+                "chunk_lnL_gpu_default_schedule": got_split, "default_schedule_launches": launches,
+                "rel_err": abs(got_walk - ref_lnl) / abs(ref_lnl),
+                "rel_err_default_schedule": abs(got_split - ref_lnl) / abs(ref_lnl),
+                "note": "same kernel instantiation as the timed run; P matrices are the reference's own (scipy expm)"}
         # MCMC generations/s through the driver on the reference's README example (config C1)
         try:
             import io
@@ -452,7 +549,7 @@ def run_ours(a):
             likelihood.reset_engines()
             os.environ["CYBAYES_COMPRESS_MAX_SITES"] = "250000"
             likelihood.COMPRESS_MAX_SITES = 250000
-            res = run_chain(os.path.join(REPO, "tests", "golden", "data", "narrow.phy"), "F81", 3000, 1000, "bin",
+            res = run_chain(os.path.join(DATA, "narrow.phy"), "F81", 3000, 1000, "bin",
                             os.path.join(tempfile.gettempdir(), "bench_narrow"), out=io.StringIO())
             out["mcmc"] = {"gens_per_sec": res["gens_per_sec"], "config": "C1 narrow.phy F81 bin Gamma-4, 3000 "
                            "generations through cybayes_b200.driver (same trace as the reference driver)",
@@ -470,12 +567,281 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------- C5
+def run_c5(a):
+    """C5: 512 taxa x 200 000 patterns x 64 states, GTR + Gamma-4 (FP64 tensor path, prune_dmma_rc_kernel<64>).
+    On one GPU the full cache (209 GB) does not fit: the step is the likelihood-only evaluation there; sharded
+    over N >= 2 GPUs (torchrun) the step keeps the cache."""
+    rank, world, local, dist = _rendezvous(a)
+    from cybayes_b200 import config, likelihood
+    from cybayes_b200.alignment import LeafMatrices
+    from cybayes_b200.ML_gamma import matML
+    from cybayes_b200.synthetic import SyntheticAlignment, shard_bounds
+    S, C, N = 64, 4, a.taxa
+    block_sites = min(a.patterns, 25000)
+    aln = SyntheticAlignment(N, a.patterns, S, 20260102, block_sites=block_sites)
+    lo, hi = shard_bounds(a.patterns, rank, world, block_sites)
+    t_gen = time.perf_counter()
+    codes = aln.codes(lo, hi)
+    t_gen = time.perf_counter() - t_gen
+    n_local = hi - lo
+    config.N_TAXA, config.N_CHARS, config.N_SITES, config.MODEL, config.IN_DTYPE = N, S, n_local, "GTR", "multi"
+    leaves = LeafMatrices(codes, S, np.ones((1, S)))
+    config.LEAF_LLMAT = leaves
+    eng, _ = likelihood.engine_for(leaves, C)
+    if world > 1:
+        box = [eng.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(box[0], rank, world)
+    edges = aln.edge_order()
+    plan = likelihood._plan_for(edges)
+    block, slots, pslots, slot_of, ekeys = _tables(eng, aln, plan, C)
+    n_e = len(ekeys)
+    pi = aln.pi
+    keep_cache = (N - 2) * C * S * n_local * 8 <= 150e9
+
+    def step():
+        lnl, snap = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=keep_cache)
+        if snap >= 0:
+            eng.release_snapshot(snap)
+        return lnl
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+    for _ in range(a.warmup):
+        lnl = step()
+    barrier()
+    eng.sync()
+    clocks = ClockSampler(local) if rank == 0 else None
+    st0 = eng.stats()
+    kernel_ms, main_ms = [], []
+    eng.mark(0)
+    for _ in range(a.steps):
+        lnl = step()
+        kernel_ms.append(eng.last_eval_ms())
+        main_ms.append(eng.last_eval_main_ms())
+    eng.mark(1)
+    eng.sync()
+    dev_ms = eng.mark_elapsed_ms()
+    st1 = eng.stats()
+    info = eng.last_eval_info()
+    barrier()
+    clock_rec = clocks.stop() if clocks else None
+    dev_ms = _max_over_ranks(dist, dev_ms)
+    ms_per_step = dev_ms / a.steps
+    n_int_edges = sum(1 for (p, c) in ekeys if c > N)
+    flops = C * n_local * (2.0 * S * S * n_int_edges + S * (N - 1) + 2.0 * S)     # SURVEY 8(d), this rank's shard
+    k_ms = statistics.mean(main_ms)
+    fp64_peak, fp64_src = eng.fp64_peak_tflops(), "measured in this run (cb_fp64_peak: DMMA m8n8k4 from registers)"
+    hbm_peak, hbm_src = measured_peaks()
+    required = info["bytes_written"] + info["bytes_read"]
+    roofline = {"bound": "tensor", "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": flops / (k_ms * 1e-3) / 1e12 / fp64_peak, "traffic": None, "kernel": "prune_dmma_rc_kernel<64, true>",
+                "algorithmic_flop_per_eval": flops, "kernel_ms_per_eval": k_ms, "peak_source": fp64_src,
+                "note": "FP64 tensor (mma.sync DMMA; tcgen05 has no fp64 kind)",
+                "hbm": {"required_bytes_per_eval": required, "GBps": required / (k_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                        "frac": required / (k_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
+                "op_list": {k: info[k] for k in ("ops", "stored", "read_back", "launches")}}
+    # end to end: reference-style host P dicts -> matML
+    host_p = eng.download_pmats(slots).reshape(C, n_e, S, S)
+    tm_host = [{e: host_p[k, i] for i, e in enumerate(ekeys)} for k in range(C)]
+    for _ in range(2):
+        l2, cache = matML(pi, aln.root, leaves, edges, tm_host, n_local, N, C)
+        del cache
+    barrier()
+    eng.sync()
+    s0 = eng.stats()
+    t0 = time.perf_counter()
+    n_e2e = max(3, a.steps // 4)
+    for _ in range(n_e2e):
+        l2, cache = matML(pi, aln.root, leaves, edges, tm_host, n_local, N, C)
+        del cache
+    e2e_s = _max_over_ranks(dist, (time.perf_counter() - t0) / n_e2e)
+    s1 = eng.stats()
+    assert abs(l2 - lnl) <= 1e-12 * abs(lnl), (l2, lnl)
+    out = {"metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(a), "lnL": lnl,
+           "cache_kept": bool(keep_cache), "roofline": roofline,
+           "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) / n_e2e,
+                   "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) / n_e2e,
+                   "note": "host P matrices (134 MB) + op list in, lnL out; matML keeps the cache when it fits, else "
+                           "evaluates the likelihood and materialises the cache on first use"},
+           "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"], "clocks": clock_rec,
+           "data_generation_s": t_gen}
+    if rank == 0 and world == 1 and not a.no_extras:
+        chunk = min(2000, n_local)
+        base, ref_lnl, ref_mats = cpu_baseline_chunk(a, S, 20260102, chunk, reps=2)
+        out["cpu_baseline"] = base
+        if ref_lnl is not None:
+            from cybayes_b200.engine import Engine
+            os.environ["CYBAYES_DMMA_RC"] = "1"
+            e2 = Engine(np.ascontiguousarray(aln.codes(0, block_sites)[:, :chunk]), S, C, device=local)
+            del os.environ["CYBAYES_DMMA_RC"]
+            b2 = e2.alloc_slots(n_e * C)
+            e2.upload_pmats(np.arange(b2.base, b2.base + n_e * C, dtype=np.int32), ref_mats)
+            got, _ = e2.eval(None, plan.nodes, plan.children, pslots - block.base + b2.base, pi, want_snapshot=False)
+            e2.close()
+            out["cpu_baseline"]["parity"] = {"chunk_sites": chunk, "chunk_lnL_reference": ref_lnl, "chunk_lnL_gpu": got,
+                                             "rel_err": abs(got - ref_lnl) / abs(ref_lnl)}
+    elif rank == 0:
+        out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "reported at N=1 only"}
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ C1 - C3
+def _reference_real(fname, reader, dtype, model, n_gen):
+    """The compiled reference, 1 core, fresh interpreter: ms per full matML / cache_matML and generations/s of its
+    own driver loop on the real dataset."""
+    code = f'''
+import sys, io, time, random, contextlib, json, runpy
+import numpy as np
+sys.path.insert(0, {os.path.join(REPO, "oracle", "_ref")!r})
+import config, utils, mcmc_gamma, ML_gamma
+np.random.seed(1234); random.seed(1234)
+with contextlib.redirect_stdout(io.StringIO()):
+    (config.N_TAXA, config.N_CHARS, config.ALPHABET, sd, config.LEAF_LLMAT, config.TAXA, config.N_SITES) = utils.{reader}({os.path.join(DATA, fname)!r})
+config.IN_DTYPE, config.MODEL, config.N_NODES = {dtype!r}, {model!r}, 2 * config.N_TAXA - 1
+st = mcmc_gamma.state_init()
+a = (config.N_SITES, config.N_TAXA, config.N_CATS)
+lnl, cache = ML_gamma.matML(st["pi"], st["root"], config.LEAF_LLMAT, st["postorder"], st["transitionMat"], *a)
+t = []
+for _ in range(5):
+    t0 = time.perf_counter(); ML_gamma.matML(st["pi"], st["root"], config.LEAF_LLMAT, st["postorder"], st["transitionMat"], *a); t.append(time.perf_counter() - t0)
+rev = mcmc_gamma.adjlist2reverse_nodes_dict(st["tree"])
+td = []
+rng = random.Random(3)
+for _ in range(20):
+    p, c = rng.choice(list(st["tree"]))
+    path = mcmc_gamma.get_path2root(rev, c, st["root"])
+    t0 = time.perf_counter(); ML_gamma.cache_matML(st["pi"], st["root"], config.LEAF_LLMAT, cache, path, st["postorder"], st["transitionMat"], *a); td.append(time.perf_counter() - t0)
+gps = None
+if {reader!r} != "readPhy":
+    sys.argv = ["mat_mcmc_gamma.py", "-i", {os.path.join(DATA, fname)!r}, "-m", {model!r}, "-n", "{n_gen}", "-t", "1000", "-d", {dtype!r}, "-o", "/tmp/bench_ref_real"]
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        runpy.run_path({os.path.join(REPO, "oracle", "_ref", "mat_mcmc_gamma.code")!r}, run_name="__main__")
+    gps = {n_gen} / (time.perf_counter() - t0)
+print("@@" + json.dumps([sorted(t)[len(t)//2] * 1e3, sum(td) / len(td) * 1e3, float(lnl), gps]))
+'''
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    line = [l for l in res.stdout.splitlines() if l.startswith("@@")]
+    return json.loads(line[0][2:]) if line else None
+
+
+def run_real(a):
+    """C1 - C3: the real datasets (latency-bound, cache 8-90 MB).  metric = MCMC generations/s through the restated
+    driver on the CUDA engine (value, fast driver; e2e = the reference's own unmodified script on the compat
+    modules where its reader can parse the file), with us per full / dirty-path evaluation and batched proposal
+    scoring beside it."""
+    import io
+    import random
+    from cybayes_b200 import config, likelihood
+    from cybayes_b200.driver import load_alignment, run_chain
+    from cybayes_b200.mcmc_gamma import adjlist2reverse_nodes_dict, get_path2root, state_init
+    from cybayes_b200.ML_gamma import cache_matML, matML
+    os.environ["CYBAYES_COMPRESS_MAX_SITES"] = "250000"
+    likelihood.COMPRESS_MAX_SITES = 250000
+    fname, reader, dtype, model = REAL[a.config]
+    likelihood.reset_engines()
+    np.random.seed(1234)
+    random.seed(1234)
+    load_alignment(os.path.join(DATA, fname), dtype, reader)
+    config.MODEL = model
+    st = state_init()
+    args = (config.N_SITES, config.N_TAXA, config.N_CATS)
+    lnl, cache = matML(st["pi"], st["root"], config.LEAF_LLMAT, st["postorder"], st["transitionMat"], *args)
+    eng, _ = likelihood.engine_for(config.LEAF_LLMAT, config.N_CATS)
+    clocks = ClockSampler(int(os.environ.get("CYBAYES_DEVICE", "0")))
+    wall, dev = [], []
+    for _ in range(a.warmup + 30):
+        t0 = time.perf_counter()
+        l2, c2 = matML(st["pi"], st["root"], config.LEAF_LLMAT, st["postorder"], st["transitionMat"], *args)
+        wall.append(time.perf_counter() - t0)
+        dev.append(eng.last_eval_ms())
+        del c2
+    info_full = eng.last_eval_info()
+    parents = adjlist2reverse_nodes_dict(st["tree"])
+    rng = random.Random(3)
+    dwall, ddev, dlen = [], [], []
+    for _ in range(40):
+        p, c = rng.choice(list(st["tree"]))
+        path = get_path2root(parents, c, st["root"])
+        t0 = time.perf_counter()
+        l3, c3 = cache_matML(st["pi"], st["root"], config.LEAF_LLMAT, cache, path, st["postorder"], st["transitionMat"], *args)
+        dwall.append(time.perf_counter() - t0)
+        ddev.append(eng.last_eval_ms())
+        dlen.append(len(path))
+        assert l3 == lnl
+        del c3
+    wall, dev = wall[a.warmup:], dev[a.warmup:]
+    n_states, n_patterns, n_taxa, n_sites = config.N_CHARS, eng.n_patterns, config.N_TAXA, config.N_SITES
+    likelihood.reset_engines()
+    n_gen = {"C1": 20000, "C2": 4000, "C3": 4000}[a.config]
+    res = run_chain(os.path.join(DATA, fname), model, n_gen, 1000, dtype, os.path.join(tempfile.gettempdir(), "b_" + a.config),
+                    reader=reader, out=io.StringIO(), fast_spr=True)
+    gens = res["gens_per_sec"]
+    fast = None
+    try:
+        from cybayes_b200.fastchain import run_chain_native
+        likelihood.reset_engines()
+        r2 = run_chain_native(os.path.join(DATA, fname), model, n_gen, 1000, dtype,
+                              os.path.join(tempfile.gettempdir(), "bn_" + a.config), reader=reader, out=io.StringIO())
+        fast = {"gens_per_sec": r2["gens_per_sec"], "same_final_lnL": float(r2["state"]["logLikehood"]) == float(res["state"]["logLikehood"])}
+    except ImportError:
+        pass
+    clock_rec = clocks.stop()
+    peak, peak_src = measured_peaks()
+    req = info_full["bytes_written"] + info_full["bytes_read"]
+    d_us = statistics.median(dev) * 1e3
+    ref = _reference_real(fname, reader, dtype, model, min(n_gen, 3000)) if reference_available() and not a.no_extras else None
+    value = fast["gens_per_sec"] if fast else gens
+    out = {"metric": "MCMC generations/sec", "value": value, "unit": "gens/s", "n_gpus": 1, "steps": n_gen, "warmup": a.warmup,
+           "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None,
+           "dtype": "f64", "data": f"tests/golden/data/{fname} (reference dataset)",
+           "config": {"workload": f"{a.config}: {fname} {model} + Gamma-4 MCMC, {n_gen} generations, seed 1234",
+                      "n_taxa": n_taxa, "n_sites": n_sites, "n_patterns": n_patterns, "n_states": n_states,
+                      "l2": "whole partial cache is L2-resident (8-90 MB): latency-bound, no flush"},
+           "driver_py": {"gens_per_sec": gens, "note": "cybayes_b200.driver (restated MH loop, Python) with dirty-path SPR"},
+           "native_loop": fast,
+           "full_eval": {"device_us": d_us, "call_us": statistics.median(wall) * 1e6},
+           "dirty_path": {"device_us": statistics.median(ddev) * 1e3, "call_us": statistics.median(dwall) * 1e6,
+                          "mean_path_nodes": statistics.mean(dlen)},
+           "roofline": {"bound": "hbm", "achieved": req / (d_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": req / (d_us * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                        "note": "launch-latency-bound (SURVEY 8d): the cache is L2-resident; absolute us per "
+                                "evaluation is the figure of merit, the fraction is given for completeness"},
+           "e2e": {"value": value, "unit": "gens/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": 8,
+                   "note": "every generation uploads op descriptors + new P scalars and reads lnL back"},
+           "clocks": clock_rec, "lnL_initial": float(lnl)}
+    if ref:
+        out["cpu_baseline"] = {"value": ref[3], "unit": "gens/s", "cores": 1, "kind": "reference",
+                               "sample": f"the reference's own driver, {min(n_gen, 3000)} generations, 1 core "
+                                         "(None where its reader cannot parse the file, SURVEY F4)",
+                               "full_eval_ms": ref[0], "dirty_path_ms": ref[1],
+                               "lnL_rel_err": abs(float(lnl) - ref[2]) / abs(ref[2])}
+    print(json.dumps(out))
+
+
 def main():
     a = parse()
     if a.impl == "reference":
+        if a.config in REAL:
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm of C1-C3 is reported inside "
+                              "cpu_baseline of the --config line (its driver is single-process)"}))
+            return
         run_reference_arm(a)
+    elif a.config == "C4":
+        run_c4(a)
+    elif a.config == "C5":
+        run_c5(a)
     else:
-        run_ours(a)
+        run_real(a)
 
 
 if __name__ == "__main__":

@@ -38,6 +38,8 @@ SIGNATURES = {
     "cb_snapshot_read": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_f64p, c_i32p]),
     "cb_stats": (C.c_int, [C.c_void_p, c_i64p, c_i64p, c_i64p, c_i64p]),
     "cb_last_eval_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "cb_last_eval_main_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "cb_last_eval_info": (C.c_int, [C.c_void_p, c_i64p, c_i64p, c_i32p]),
     "cb_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "cb_mark_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cb_sync": (C.c_int, [C.c_void_p]),

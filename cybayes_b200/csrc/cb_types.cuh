@@ -8,7 +8,8 @@ namespace cb {
 // SRC_CHERRY (2-state family only): the child is a "cherry" -- an internal node whose two children are
 // tips.  Its partial has only 3 x 3 possible values per rate category (state code of either tip: 0, 1,
 // missing), so it is never computed per site, stored or read: the parent looks its contribution up.
-enum SrcKind : int32_t { SRC_TIP = 0, SRC_BUFFER = 1, SRC_CARRIED = 2, SRC_CHERRY = 3 };
+// SRC_STACK (tiled 2-state kernel only): the child was pushed into a shared-memory tile buffer by an earlier op of the walk.
+enum SrcKind : int32_t { SRC_TIP = 0, SRC_BUFFER = 1, SRC_CARRIED = 2, SRC_CHERRY = 3, SRC_STACK = 4 };
 
 constexpr int CB_S2_MAX_CATS = 4;            // rate categories of the 2-state kernels (1 or 4)
 constexpr int32_t CB_LIB_SLOT = 1 << 30;     // P-slot ids with this bit address the library's own pool
@@ -28,7 +29,11 @@ struct OpDesc {
   const void* ctip[2][2];                  // code rows of the cherry's two tips
   int32_t cslot[2][2][CB_S2_MAX_CATS];     // P slots of the cherry's two tip edges, per category
   int32_t crec_out[2];                     // library record that must keep a copy of those P, or -1
-  int32_t pad2_[6];
+  // tiled 2-state kernel (kernels_s2t.cuh)
+  int32_t out_buf;                         // shared-memory tile buffer receiving the result, or -1
+  int32_t in_buf[2];                       // kind == SRC_STACK: tile buffer holding the child
+  int32_t spill;                           // stored AND read back inside the same launch: plain stores
+  int32_t pad2_[2];
 };
 static_assert(sizeof(OpDesc) == 256, "OpDesc must stay 256 bytes");
 

@@ -26,6 +26,7 @@
 #include "kernels_general.cuh"
 #include "kernels_pmat.cuh"
 #include "kernels_s2.cuh"
+#include "kernels_s2t.cuh"
 
 using namespace cb;
 
@@ -99,6 +100,7 @@ enum { NCCL_DOUBLE = 8, NCCL_SUM = 0 };  // ncclFloat64 / ncclSum in nccl.h
 // ------------------------------------------------------------------------------ context
 constexpr int DMMA_RC_MIN_STATES = 9;   // measured: 1.65x (S = 23, 2304 patterns) .. 3.1x (S = 30, 16384) over the plain FP64 kernel
 constexpr int64_t DMMA_RC_MIN_SITES = 1024;  // measured crossover against the 64-site tile kernel + level schedule (S = 47, 64)
+constexpr int64_t S2_TILED_MIN_SITES = 64 * 2 * 148 * 4;  // 75 776: from here a 2-state alignment fills the GPU with 256-site blocks
 
 struct Buffer {
   double* data = nullptr;
@@ -117,6 +119,36 @@ struct CherryRec {
   int refs = 0;
 };
 
+// ---- evaluation plans (see build_plan)
+struct PlanChild {
+  int32_t kind;  // SrcKind
+  int32_t ref;   // SRC_TIP: tip id.  SRC_BUFFER: position of the producing op, or ~node (< 0) when the input snapshot
+                 // holds it.  SRC_CHERRY: caller's op index of the folded cherry, or ~node for a record of the input
+                 // snapshot.  SRC_STACK: tile buffer.  SRC_CARRIED: unused.
+  int32_t edge;  // 2 * (caller's op index) + child: where this edge's P slots sit in the caller's arrays
+};
+struct PlanOp {
+  int32_t node;
+  PlanChild ch[2];
+  int32_t out_buf;               // tiled kernel: shared-memory tile buffer of the result, or -1
+  uint8_t is_root, keep, stream, spill;
+};
+struct PlanLaunch { int r_begin, r_end, max_ops, n_bufs; };
+struct EvalPlan {
+  // key (full evaluations only)
+  int flags = 0, n_lists = 0, split_env = 0;
+  std::vector<int32_t> key_offsets, key_nodes, key_children;
+  // compiled form
+  std::vector<PlanOp> ops;
+  std::vector<RangeDesc> ranges;
+  std::vector<PlanLaunch> launches;
+  int64_t bytes_written = 0, bytes_read = 0;
+  int n_stored = 0, n_buffer_reads = 0, n_stack = 0, n_spills = 0, n_cherries = 0;
+  uint64_t stamp = 0;
+};
+constexpr int PLAN_FLAG_MASK = CB_EVAL_WANT_SNAPSHOT | CB_EVAL_STORE_ROOT | CB_EVAL_FORCE_LEVELS | CB_EVAL_FORCE_WALK | CB_EVAL_NO_FOLD;
+constexpr int PLAN_CACHE_SIZE = 6;
+
 struct cb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -131,6 +163,9 @@ struct cb_ctx {
   int rc_stagger = 1;     // anti-lockstep barriers between the warps of one SM sub-partition, see kernels_dmma_rc.cuh
   double* d_staged = nullptr;  // P matrices of the current evaluation in stage layout and consumption order
   size_t staged_bytes = 0;
+  bool s2_tiled = false;  // 2-state family on a large alignment: tile-interleaved partials + prune_s2t_kernel
+  int s2t_slots = 3;      // its shared-memory stack slots per warp (tile buffers 2 .. 2 + slots - 1)
+  S2TImage* d_images = nullptr;  // op images of the current evaluation (s2t_image_kernel)
   int s2_vec = 1;  // sites per thread of the 2-state kernel on large alignments
   int s2_minb = 3; // its __launch_bounds__ min blocks per SM (experiment knob)
   bool s2_stream_stores = true;  // st.global.cs for partials the walk never reads back (10.67 vs 11.0 ms on C4)
@@ -176,8 +211,15 @@ struct cb_ctx {
   // NCCL
   ncclComm_t comm = nullptr;
   int n_ranks = 1;
-  // work vectors reused across evals
-  std::vector<int32_t> op_of_node, level_of_op, order;
+  // plans of full evaluations, cached per topology; scratch plan of dirty-path evaluations
+  std::vector<EvalPlan> plans;
+  EvalPlan scratch_plan;
+  uint64_t plan_clock = 0, plan_builds = 0;
+  bool no_plan_cache = false;
+  std::vector<int> work_new_bufs, work_new_nodes, work_cherry_nodes;
+  cudaEvent_t ev_main0 = nullptr, ev_main1 = nullptr;  // around the pruning launches proper (without pre-passes)
+  int64_t last_bytes_written = 0, last_bytes_read = 0;
+  int32_t last_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // stats
   int64_t launches = 0, h2d = 0, d2h = 0, dev_bytes = 0;
   bool timing_valid = false;
@@ -223,12 +265,18 @@ static int create_impl(int device, cb_ctx** out) {
   CU(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev_mark[0]));
   CU(cudaEventCreate(&c->ev_mark[1]));
+  CU(cudaEventCreate(&c->ev_main0));
+  CU(cudaEventCreate(&c->ev_main1));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   if (const char* v = getenv("CYBAYES_S2_V")) c->s2_vec = (atoi(v) == 2) ? 2 : 1;
   if (const char* v = getenv("CYBAYES_S2_MINB")) c->s2_minb = (atoi(v) == 4) ? 4 : 3;
   if (getenv("CYBAYES_S2_NO_CS")) c->s2_stream_stores = false;
+  if (const char* v = getenv("CYBAYES_S2T_SLOTS")) c->s2t_slots = std::max(0, std::min(8, atoi(v)));
+  if (getenv("CYBAYES_NO_PLAN_CACHE")) c->no_plan_cache = true;
+  CU(cudaFuncSetAttribute(prune_s2t_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));  // + 384 B static
+  CU(cudaFuncSetAttribute(prune_s2t_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   CU(cudaFuncSetAttribute(prune_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #define CB_DMMA_ATTR(SS) CU(cudaFuncSetAttribute(prune_dmma_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
   CB_DMMA_ATTR(0); CB_DMMA_ATTR(32); CB_DMMA_ATTR(40); CB_DMMA_ATTR(47); CB_DMMA_ATTR(48); CB_DMMA_ATTR(56); CB_DMMA_ATTR(64);
@@ -244,6 +292,14 @@ static int create_impl(int device, cb_ctx** out) {
 }
 
 static void free_alignment(cb_ctx* c) {
+  c->plans.clear();
+  if (c->d_images) {  // sized with the op staging area: both are re-created on demand
+    dev_free(c, c->d_images, (size_t)c->ops_cap * sizeof(S2TImage));
+    c->d_images = nullptr;
+    if (c->d_ops) dev_free(c, c->d_ops, (size_t)c->ops_cap * sizeof(OpDesc));
+    if (c->h_ops) cudaFreeHost(c->h_ops);
+    c->d_ops = nullptr; c->h_ops = nullptr; c->ops_cap = 0;
+  }
   for (auto& b : c->buffers) dev_free(c, b.data, c->buffer_bytes);
   c->buffers.clear();
   c->free_buffers.clear();
@@ -285,6 +341,7 @@ extern "C" int cb_destroy(cb_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   free_alignment(c);
   if (c->d_ops) dev_free(c, c->d_ops, (size_t)c->ops_cap * sizeof(OpDesc));
+  if (c->d_images) dev_free(c, c->d_images, (size_t)c->ops_cap * sizeof(S2TImage));
   if (c->d_ranges) dev_free(c, c->d_ranges, (size_t)c->ranges_cap * sizeof(RangeDesc));
   if (c->h_ops) cudaFreeHost(c->h_ops);
   if (c->h_ranges) cudaFreeHost(c->h_ranges);
@@ -296,6 +353,8 @@ extern "C" int cb_destroy(cb_ctx* c) {
   cudaEventDestroy(c->ev_stage);
   cudaEventDestroy(c->ev_mark[0]);
   cudaEventDestroy(c->ev_mark[1]);
+  cudaEventDestroy(c->ev_main0);
+  cudaEventDestroy(c->ev_main1);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -367,6 +426,16 @@ static int set_tips_impl(cb_ctx* c, int n_taxa, int64_t n_sites, int n_states, i
   c->n_amb = n_amb;
   c->P = (n_sites + 63) / 64 * 64;
   c->family_s2 = (n_states == 2 && (n_cats == 4 || n_cats == 1));
+  {
+    // large binary alignments use the tiled kernel (kernels_s2t.cuh); CYBAYES_S2_TILED=1/0 forces it on / off (tests)
+    const char* v = getenv("CYBAYES_S2_TILED");
+    c->s2_tiled = c->family_s2 && code_bytes == 1 && (v ? atoi(v) != 0 : c->P >= S2_TILED_MIN_SITES);
+    if (c->s2_tiled && c->ops_cap > 0 && !c->d_images) {  // staging sized before this alignment: re-create it with images
+      if (c->d_ops) dev_free(c, c->d_ops, (size_t)c->ops_cap * sizeof(OpDesc));
+      if (c->h_ops) cudaFreeHost(c->h_ops);
+      c->d_ops = nullptr; c->h_ops = nullptr; c->ops_cap = 0;
+    }
+  }
   c->use_dmma = !c->family_s2 && n_states >= 32 && n_states <= 64 && !getenv("CYBAYES_NO_DMMA");
   {
     // The kernel is fixed per alignment (never per schedule), so every evaluation of an alignment sums in one order.
@@ -604,9 +673,24 @@ static int snapshot_read_impl(cb_ctx* c, int s, int node, double* out, int32_t* 
   std::vector<double> tmp((size_t)C * S * P);
   const size_t n_scale = c->family_s2 ? (size_t)P : (size_t)C * P;
   std::vector<int32_t> sc(n_scale);
-  CU(cudaMemcpyAsync(tmp.data(), b.data, tmp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(sc.data(), b.scale, n_scale * 4, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  if (c->s2_tiled) {
+    // tile-interleaved layout (kernels_s2t.cuh): per 32 sites, 2C rows of 32 doubles then 32 exponents
+    std::vector<unsigned char> raw(c->buffer_bytes);
+    CU(cudaMemcpyAsync(raw.data(), b.data, raw.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const size_t TB = (size_t)s2t_tile_bytes(C);
+    for (int64_t t = 0; t < P / S2T_W; ++t) {
+      const double* rows = reinterpret_cast<const double*>(raw.data() + (size_t)t * TB);
+      const int32_t* ex = reinterpret_cast<const int32_t*>(rows + (size_t)2 * C * S2T_W);
+      for (int r = 0; r < 2 * C; ++r)
+        for (int l = 0; l < S2T_W; ++l) tmp[(size_t)r * P + t * S2T_W + l] = rows[(size_t)r * S2T_W + l];
+      for (int l = 0; l < S2T_W; ++l) sc[(size_t)t * S2T_W + l] = ex[l];
+    }
+  } else {
+    CU(cudaMemcpyAsync(tmp.data(), b.data, tmp.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(sc.data(), b.scale, n_scale * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
   c->d2h += (int64_t)tmp.size() * 8 + (int64_t)n_scale * 4;
   for (int k = 0; k < C; ++k)
     for (int i = 0; i < S; ++i)
@@ -643,9 +727,11 @@ static int ensure_staging(cb_ctx* c, int n_ops, int n_ranges, int n_out) {
     int cap = std::max(n_ops, std::max(256, c->ops_cap * 2));
     CU(cudaStreamSynchronize(c->stream));
     if (c->d_ops) dev_free(c, c->d_ops, (size_t)c->ops_cap * sizeof(OpDesc));
+    if (c->d_images) dev_free(c, c->d_images, (size_t)c->ops_cap * sizeof(S2TImage));
     if (c->h_ops) cudaFreeHost(c->h_ops);
-    c->d_ops = nullptr; c->h_ops = nullptr; c->ops_cap = 0;
+    c->d_ops = nullptr; c->h_ops = nullptr; c->d_images = nullptr; c->ops_cap = 0;
     if (dev_alloc(c, (void**)&c->d_ops, (size_t)cap * sizeof(OpDesc))) return 1;
+    if (c->s2_tiled && dev_alloc(c, (void**)&c->d_images, (size_t)cap * sizeof(S2TImage))) return 1;
     CU(cudaMallocHost(&c->h_ops, (size_t)cap * sizeof(OpDesc)));
     c->ops_cap = cap;
   }
@@ -726,17 +812,26 @@ static int general_rows_per_chunk(int S) {
   return 0;
 }
 
-// Launch the ranges [r_begin, r_end) (all independent) as one kernel.
-static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end, int max_ops_in_range) {
+// Launch the ranges [r_begin, r_end) (all independent) as one kernel.  n_bufs: shared-memory tile buffers per
+// warp the ops of these ranges name (tiled 2-state kernel only).
+static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end, int max_ops_in_range, int n_bufs) {
   const int n_r = r_end - r_begin;
   LaunchConst kk = k;
   kk.ranges = k.ranges + r_begin;
-  if (c->family_s2) {
+  if (c->s2_tiled) {
+    // large binary alignments: tile-interleaved partials, shared-memory stack, bulk-async stores (kernels_s2t.cuh)
+    const size_t smem = s2t_smem_bytes(n_bufs, c->n_cats);
+    REQUIRE(smem <= (size_t)226 * 1024, "internal error: %d tile buffers do not fit shared memory", n_bufs);
+    const int64_t n_tiles = c->P / S2T_W;
+    dim3 grid((unsigned)((n_tiles + S2T_WARPS - 1) / S2T_WARPS), (unsigned)n_r);
+    if (c->n_cats == 4) prune_s2t_kernel<4><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
+    else prune_s2t_kernel<1><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
+  } else if (c->family_s2) {
     // Fixed per alignment (independent of the schedule) so the reduction order never changes:
-    // big alignments: 256 threads x V sites (V from CYBAYES_S2_V, default 1 = more resident warps);
-    // small alignments: 64-thread blocks, one site per thread, to spread over the SMs.
+    // 64-thread blocks, one site per thread, to spread a small alignment over the SMs (the tiled kernel above
+    // takes over from 75 776 patterns); CYBAYES_S2_TILED=0 keeps this kernel on large alignments too (256 threads).
     const size_t smem = s2_smem_bytes(max_ops_in_range, c->n_cats);
-    const bool small = c->P < (int64_t)64 * 2 * c->sm_count * 4;
+    const bool small = c->P < S2_TILED_MIN_SITES;
     const int V = small ? 1 : c->s2_vec;
     const int threads = small ? 64 : 256;
     dim3 grid((unsigned)((c->P + (int64_t)threads * V - 1) / ((int64_t)threads * V)), (unsigned)n_r);
@@ -782,6 +877,16 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
   return 0;
 }
 
+// tiled 2-state kernel: build the op images of ops [0, n_ops) (one launch per evaluation)
+static int launch_images(cb_ctx* c, const LaunchConst& k, int n_ops) {
+  if (!c->s2_tiled) return 0;
+  if (c->n_cats == 4) s2t_image_kernel<4><<<n_ops, 32, 0, c->stream>>>(k, n_ops, c->d_images);
+  else s2t_image_kernel<1><<<n_ops, 32, 0, c->stream>>>(k, n_ops, c->d_images);
+  CU(cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+
 // Compute the partial of a folded cherry into a fresh buffer (debug / read-back path): one ordinary op
 // with two tip children whose P matrices come from the library's pool.
 static int materialize_cherry(cb_ctx* c, int rec, int* buf_out) {
@@ -794,6 +899,7 @@ static int materialize_cherry(cb_ctx* c, int rec, int* buf_out) {
   memset(&op, 0, sizeof op);
   op.dst = c->buffers[bi].data;
   op.dst_scale = c->buffers[bi].scale;
+  op.out_buf = -1;
   for (int kx = 0; kx < 2; ++kx) {
     op.kind[kx] = SRC_TIP;
     op.src[kx] = (const char*)c->d_codes + (size_t)(c->recs[rec].tip[kx] - 1) * c->P * c->code_bytes;
@@ -804,372 +910,549 @@ static int materialize_cherry(cb_ctx* c, int rec, int* buf_out) {
   CU(cudaMemcpyAsync(c->d_ops, c->h_ops, sizeof(OpDesc), cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->d_ranges, c->h_ranges, sizeof(RangeDesc), cudaMemcpyHostToDevice, c->stream));
   const LaunchConst k = make_const(c);
-  if (launch_ranges(c, k, 0, 1, 1)) return 1;
+  if (launch_images(c, k, 1)) { buffer_release(c, bi); return 1; }
+  if (launch_ranges(c, k, 0, 1, 1, 0)) { buffer_release(c, bi); return 1; }
   CU(cudaStreamSynchronize(c->stream));
   *buf_out = bi;
   return 0;
 }
 
-// Shared implementation of cb_eval (n_lists = 1) and cb_eval_batch.
+// ---- plans --------------------------------------------------------------------------------------------------
+// An evaluation is compiled into a PLAN: which ops run (cherries folded away), in which order, in which ranges
+// and launches, where every child comes from, which results are stored.  The plan of a FULL evaluation depends only
+// on the op list and the flags, so it is cached per topology (a handful of trees are alive at a time in an MCMC
+// run: the current one and the proposals); executing a cached plan only refills buffer pointers and P slots.
 //
 // Schedules (all run the same per-node arithmetic, so results are bit-identical):
 //   CHAIN  a dirty path: one launch, one block range walks the ops, the on-path partial is
 //          carried in registers / shared memory                        (ML_gamma.pyx:99-114)
-//   WALK   a whole (sub)tree on a large alignment: ONE launch; every block walks all ops for
-//          its site tile in depth-first order, heavier subtree first.  The child finished
-//          last is carried on chip, so only nodes with two internal children are ever read
-//          back (about a third of them), and those reads come from this block's own recent
-//          writes (L2) when the lighter sibling subtree is small.
+//   WALK   a whole (sub)tree in ONE launch; every block walks all ops for its site tile depth-first.  The child
+//          finished last is carried on chip; the other child of a node with two internal children is pushed on a
+//          stack in shared memory (tiled 2-state kernel: K tile buffers per warp) or, when the stack is full or the
+//          kernel has none, written to its buffer and read back.  The visiting order minimises those read-backs
+//          (dynamic programme over the tree; ties: heavier subtree first, so a read-back finds its line in L2).
 //   LEVELS one launch per tree level, grid.y = nodes of the level: the latency schedule for
 //          small alignments where a site tile alone cannot fill the GPU.
 enum Schedule { SCHED_CHAIN = 0, SCHED_WALK = 1, SCHED_LEVELS = 2 };
 
+
+static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t* offsets_in, const int32_t* nodes_in,
+                      const int32_t* children_in, int flags, EvalPlan& plan) {
+  const int N = c->n_taxa, n_nodes = 2 * N;  // ids 1 .. 2N-1
+  const bool fold = c->family_s2 && !(flags & CB_EVAL_NO_FOLD);
+  const bool want_snap = (flags & CB_EVAL_WANT_SNAPSHOT) != 0;
+  const bool store_root = (flags & CB_EVAL_STORE_ROOT) != 0;
+  const int K = c->s2_tiled ? c->s2t_slots : 0;  // stack slots of the kernel
+  plan.ops.clear(); plan.ranges.clear(); plan.launches.clear();
+  plan.bytes_written = plan.bytes_read = 0;
+  plan.n_stored = plan.n_buffer_reads = plan.n_stack = plan.n_spills = plan.n_cherries = 0;
+  const int64_t tip_row_bytes = c->P * c->code_bytes;
+
+  struct LOp { int32_t node, caller; int32_t child[2], folded[2]; };
+  std::vector<LOp> L;
+  std::vector<int32_t> parent_op(n_nodes), folded_at(n_nodes), op_of_node(n_nodes, -1);
+  std::vector<int> kid[2], n_sub, order, pos_of, range_id, push_slot, first_kid, level_of, by_level;
+  std::vector<std::pair<int, int>> segs;
+  std::vector<int> seg_of;     // op -> segment (0 = top / whole list, s + 1 = cut subtree s)
+  std::vector<int> f;          // DP table [op][k]
+  std::vector<char> read_back;
+  bool single_launch = true;
+
+  for (int li = 0; li < n_lists; ++li) {
+    const int b_in = offsets_in[li], e_in = offsets_in[li + 1];
+    REQUIRE(e_in > b_in, "empty op list %d", li);
+    // ---- cherry folding (2-state family): an op whose two children are tips is not run: its parent (always in the
+    // list) takes it as a SRC_CHERRY child and looks the cherry's 3 x 3 possible partials up
+    L.clear();
+    std::fill(parent_op.begin(), parent_op.end(), -1);
+    std::fill(folded_at.begin(), folded_at.end(), -1);
+    for (int i = b_in; i < e_in; ++i)
+      for (int kx = 0; kx < 2; ++kx) {
+        const int ch = children_in[2 * i + kx];
+        REQUIRE((ch >= 1 && ch <= N) || (ch > N && ch < n_nodes), "op %d: bad child id %d", i, ch);
+        if (ch > N) parent_op[ch] = i;
+      }
+    for (int i = b_in; i < e_in; ++i) {
+      const int node = nodes_in[i], c0 = children_in[2 * i], c1 = children_in[2 * i + 1];
+      REQUIRE(node > N && node < n_nodes, "op %d: node %d is not an internal node", i, node);
+      const bool cherry = fold && c0 <= N && c1 <= N && i != e_in - 1 && parent_op[node] > i;
+      if (cherry) {
+        folded_at[node] = i;
+        plan.n_cherries++;
+        continue;
+      }
+      LOp o;
+      o.node = node;
+      o.caller = i;
+      for (int kx = 0; kx < 2; ++kx) {
+        const int ch = children_in[2 * i + kx];
+        o.child[kx] = ch;
+        o.folded[kx] = ch > N ? folded_at[ch] : -1;
+      }
+      L.push_back(o);
+    }
+    const int n = (int)L.size();
+    // producers of the children inside this list (-1: tip, folded cherry or snapshot)
+    for (int j = 0; j < n; ++j) {
+      REQUIRE(op_of_node[L[j].node] < 0, "op %d: node %d is computed twice", L[j].caller, L[j].node);
+      op_of_node[L[j].node] = j;
+    }
+    auto cleanup = [&] { for (int j = 0; j < n; ++j) op_of_node[L[j].node] = -1; };
+    kid[0].assign(n, -1);
+    kid[1].assign(n, -1);
+    for (int j = 0; j < n; ++j)
+      for (int kx = 0; kx < 2; ++kx) {
+        const int ch = L[j].child[kx];
+        if (ch > N && L[j].folded[kx] < 0 && op_of_node[ch] >= 0) {
+          if (op_of_node[ch] >= j) { cleanup(); return fail("op %d: child %d is computed after its parent", L[j].caller, ch); }
+          kid[kx][j] = op_of_node[ch];
+        } else if (ch > N && L[j].folded[kx] < 0) {
+          const bool in_snap = sin && ch < (int)sin->buf_of_node.size() &&
+                               (sin->buf_of_node[ch] >= 0 || (ch < (int)sin->cherry_of_node.size() && sin->cherry_of_node[ch] >= 0));
+          if (!in_snap) { cleanup(); return fail("op %d: child %d is neither recomputed nor in the input snapshot", L[j].caller, ch); }
+        }
+      }
+    cleanup();
+    // chain: every op after the first consumes exactly the previous op and nothing else of the list
+    bool chain = !(flags & CB_EVAL_FORCE_LEVELS) && n <= MAX_CHAIN_OPS;
+    for (int j = 0; j < n && chain; ++j) {
+      const int a0 = kid[0][j], a1 = kid[1][j];
+      if (j == 0) chain = (a0 < 0 && a1 < 0);
+      else chain = (a0 == j - 1) != (a1 == j - 1) && (a0 < 0 || a0 == j - 1) && (a1 < 0 || a1 == j - 1);
+    }
+    Schedule sched = SCHED_CHAIN;
+    if (!chain) {
+      // the register-carried kernel only pays off when the partial is carried: its alignments always walk;
+      // candidates of a batch always walk (one range per candidate)
+      const bool big = c->dmma_rc || c->P >= (c->family_s2 ? WALK_MIN_SITES_S2 : WALK_MIN_SITES_GENERAL);
+      sched = ((big || n_lists > 1 || (flags & CB_EVAL_FORCE_WALK)) && !(flags & CB_EVAL_FORCE_LEVELS)) ? SCHED_WALK : SCHED_LEVELS;
+      if (n_lists > 1 && sched == SCHED_LEVELS) return fail("cb_eval_batch: candidate %d is not a chain (level schedule forced)", li);
+    }
+
+    order.resize(n);
+    for (int j = 0; j < n; ++j) order[j] = j;
+    seg_of.assign(n, 0);
+    push_slot.assign(n, -1);
+    segs.clear();
+    if (sched == SCHED_WALK) {
+      // subtree sizes in ops (children precede parents in the caller's order)
+      n_sub.assign(n, 1);
+      for (int j = 0; j < n; ++j)
+        for (int kx = 0; kx < 2; ++kx)
+          if (kid[kx][j] >= 0) n_sub[j] += n_sub[kid[kx][j]];
+      bool rooted = (n_sub[n - 1] == n);  // every op under the last one
+      if (!rooted) {
+        REQUIRE(n_lists == 1, "cb_eval_batch: candidate %d has ops that are not under its root", li);
+        sched = SCHED_LEVELS;
+      } else {
+        // When the alignment gives too few site tiles to fill the GPU for a whole sequential walk (small shards), the
+        // tree is cut into independent subtrees of at most `limit` ops that run as parallel ranges of a first launch;
+        // the ops above the cut follow in a second launch.
+        int limit = n + 1;
+        if (n_lists == 1) {
+          const int64_t tile_sites = c->s2_tiled ? S2T_THREADS : (c->family_s2 ? (int64_t)256 * c->s2_vec : (c->dmma_rc ? RC_T : (c->use_dmma ? DM_T : GEN_T)));
+          const int64_t blocks = (c->P + tile_sites - 1) / tile_sites * (c->family_s2 ? 1 : c->n_cats);
+          const int64_t slots = (int64_t)c->sm_count * (c->s2_tiled ? 2 : (c->family_s2 ? (c->s2_vec == 1 ? 3 : 2) : (c->dmma_rc ? 1 : 2)));
+          if (blocks < 4 * slots && n >= 64 && !(flags & CB_EVAL_FORCE_WALK))
+            limit = std::max(16, std::min(256, (int)(n * blocks / (8 * slots)) + 1));
+          if (plan.split_env > 0) limit = std::max(2, plan.split_env);
+          if (limit >= n) limit = n + 1;  // nothing to cut
+        }
+        std::vector<int> cut, top, stack;
+        if (limit <= n) {
+          // walk down from the root: ops with a subtree above the limit stay in the top segment
+          stack.push_back(n - 1);
+          while (!stack.empty()) {
+            const int j = stack.back();
+            stack.pop_back();
+            if (n_sub[j] <= limit) { cut.push_back(j); continue; }
+            for (int kx = 0; kx < 2; ++kx)
+              if (kid[kx][j] >= 0) stack.push_back(kid[kx][j]);
+          }
+          std::stable_sort(cut.begin(), cut.end(), [&](int x, int y) { return n_sub[x] > n_sub[y]; });  // big first
+          // segment membership: everything under a cut root belongs to that root's segment
+          for (size_t s = 0; s < cut.size(); ++s) {
+            stack.push_back(cut[s]);
+            while (!stack.empty()) {
+              const int j = stack.back();
+              stack.pop_back();
+              seg_of[j] = (int)s + 1;
+              for (int kx = 0; kx < 2; ++kx)
+                if (kid[kx][j] >= 0) stack.push_back(kid[kx][j]);
+            }
+          }
+        }
+        // visiting order per segment: f[j][k] = fewest read-backs in j's subtree (inside its segment) with k free stack
+        // slots; of two internal children the first visited is pushed (or read back when k == 0), the second carried
+        f.assign((size_t)n * (K + 1), 0);
+        first_kid.assign((size_t)n * (K + 1), 0);
+        for (int j = 0; j < n; ++j) {
+          int a = kid[0][j], b2 = kid[1][j];
+          if (a >= 0 && seg_of[a] != seg_of[j]) a = -1;    // a cut root: lives in another launch, read from its buffer
+          if (b2 >= 0 && seg_of[b2] != seg_of[j]) b2 = -1;
+          for (int kk = 0; kk <= K; ++kk) {
+            int& fj = f[(size_t)j * (K + 1) + kk];
+            if (a >= 0 && b2 >= 0) {
+              const int k1 = kk > 0 ? kk - 1 : 0, miss = kk == 0 ? 1 : 0;
+              const int ca = f[(size_t)a * (K + 1) + kk] + miss + f[(size_t)b2 * (K + 1) + k1];
+              const int cb2 = f[(size_t)b2 * (K + 1) + kk] + miss + f[(size_t)a * (K + 1) + k1];
+              const bool a_first = ca < cb2 || (ca == cb2 && n_sub[a] >= n_sub[b2]);
+              fj = a_first ? ca : cb2;
+              first_kid[(size_t)j * (K + 1) + kk] = a_first ? 0 : 1;
+            } else if (a >= 0) {
+              fj = f[(size_t)a * (K + 1) + kk];
+            } else if (b2 >= 0) {
+              fj = f[(size_t)b2 * (K + 1) + kk];
+            }
+          }
+        }
+        std::vector<int> out;
+        out.reserve(n);
+        struct Frame { int j, k, phase; };
+        std::vector<Frame> fr;
+        auto emit = [&](int root_op) {
+          fr.push_back({root_op, K, 0});
+          while (!fr.empty()) {
+            Frame& t = fr.back();
+            const int j = t.j, kk = t.k;
+            int a = kid[0][j], b2 = kid[1][j];
+            if (a >= 0 && seg_of[a] != seg_of[j]) a = -1;
+            if (b2 >= 0 && seg_of[b2] != seg_of[j]) b2 = -1;
+            if (a >= 0 && b2 >= 0) {
+              const int fk = first_kid[(size_t)j * (K + 1) + kk];
+              const int x = fk == 0 ? a : b2, y = fk == 0 ? b2 : a;
+              if (t.phase == 0) { t.phase = 1; fr.push_back({x, kk, 0}); continue; }
+              if (t.phase == 1) {
+                push_slot[x] = kk > 0 ? S2T_STAGING + (K - kk) : -1;
+                t.phase = 2;
+                fr.push_back({y, kk > 0 ? kk - 1 : 0, 0});
+                continue;
+              }
+            } else if (a >= 0 || b2 >= 0) {
+              if (t.phase == 0) { t.phase = 2; fr.push_back({a >= 0 ? a : b2, kk, 0}); continue; }
+            }
+            out.push_back(j);
+            fr.pop_back();
+          }
+        };
+        if (limit > n) {
+          emit(n - 1);
+        } else {
+          for (int r : cut) {
+            const int b0 = (int)out.size();
+            emit(r);
+            segs.push_back({b0, (int)out.size()});
+          }
+          emit(n - 1);
+        }
+        REQUIRE((int)out.size() == n, "internal error: walk order covers %d of %d ops", (int)out.size(), n);
+        order = out;
+      }
+    }
+    pos_of.assign(n, 0);
+    for (int p = 0; p < n; ++p) pos_of[order[p]] = p;
+    range_id.assign(n, 0);   // by position
+    for (size_t si = 0; si < segs.size(); ++si)
+      for (int p = segs[si].first; p < segs[si].second; ++p) range_id[p] = (int)si + 1;
+    // launch of a position: split walk = cut segments first (0), top second (1); levels: see below
+    auto same_range = [&](int p0, int p1) { return sched != SCHED_LEVELS && range_id[p0] == range_id[p1]; };
+
+    // where does each child come from; which ops are read back from memory by a later op?
+    read_back.assign(n, 0);
+    const int base = (int)plan.ops.size();
+    plan.ops.resize(base + n);
+    int staging_rr = 0;
+    for (int p = 0; p < n; ++p) {
+      const int j = order[p];
+      PlanOp& po = plan.ops[base + p];
+      po.node = L[j].node;
+      po.is_root = (j == n - 1);
+      REQUIRE(!po.is_root || p == n - 1, "internal error: root is not last");
+      po.keep = po.stream = po.spill = 0;
+      po.out_buf = -1;
+      for (int kx = 0; kx < 2; ++kx) {
+        PlanChild& pc = po.ch[kx];
+        const int ch = L[j].child[kx];
+        pc.edge = 2 * L[j].caller + kx;
+        if (ch <= N) {
+          pc.kind = SRC_TIP;
+          pc.ref = ch;
+          plan.bytes_read += tip_row_bytes;
+        } else if (L[j].folded[kx] >= 0) {
+          pc.kind = SRC_CHERRY;
+          pc.ref = L[j].folded[kx];
+          plan.bytes_read += 2 * tip_row_bytes;
+        } else if (kid[kx][j] >= 0) {
+          const int jj = kid[kx][j], pp = pos_of[jj];
+          if (same_range(pp, p) && pp == p - 1) {
+            pc.kind = SRC_CARRIED;
+            pc.ref = 0;
+          } else if (same_range(pp, p) && push_slot[jj] >= 0) {
+            pc.kind = SRC_STACK;
+            pc.ref = push_slot[jj];
+            plan.n_stack++;
+          } else {
+            REQUIRE(pp < p, "internal error: producer of node %d runs after its consumer", ch);
+            pc.kind = SRC_BUFFER;
+            pc.ref = base + pp;
+            read_back[jj] = same_range(pp, p) ? 2 : 1;   // 2: inside one launch (a spill)
+            plan.bytes_read += (int64_t)c->buffer_bytes;
+            plan.n_buffer_reads++;
+          }
+        } else {
+          const bool rec = fold && sin && ch < (int)sin->cherry_of_node.size() && sin->cherry_of_node[ch] >= 0;
+          pc.kind = rec ? SRC_CHERRY : SRC_BUFFER;
+          pc.ref = ~ch;
+          plan.bytes_read += rec ? 2 * tip_row_bytes : (int64_t)c->buffer_bytes;
+          if (!rec) plan.n_buffer_reads++;
+        }
+      }
+    }
+    plan.bytes_read += c->P * 8;  // pattern weights at the root
+    for (int p = 0; p < n; ++p) {
+      const int j = order[p];
+      PlanOp& po = plan.ops[base + p];
+      po.keep = po.is_root ? (want_snap && store_root) : (want_snap || read_back[j] != 0);
+      po.stream = (po.keep && read_back[j] == 0 && c->s2_stream_stores) ? 1 : 0;
+      po.spill = (read_back[j] == 2) ? 1 : 0;
+      if (po.keep) {
+        plan.bytes_written += (int64_t)c->buffer_bytes;
+        plan.n_stored++;
+        if (po.spill) plan.n_spills++;
+      }
+      if (c->s2_tiled) {
+        if (push_slot[j] >= 0 && !po.is_root) po.out_buf = push_slot[j];
+        else if (po.keep && !po.spill) { po.out_buf = staging_rr; staging_rr ^= 1; }
+      }
+    }
+
+    // ranges and launches
+    auto bufs_of = [&](int p0, int p1) {
+      int nb = 0;
+      for (int p = p0; p < p1; ++p) {
+        const PlanOp& po = plan.ops[base + p];
+        nb = std::max(nb, po.out_buf + 1);
+        for (int kx = 0; kx < 2; ++kx)
+          if (po.ch[kx].kind == SRC_STACK) nb = std::max(nb, po.ch[kx].ref + 1);
+      }
+      return nb;
+    };
+    if (sched == SCHED_WALK && !segs.empty()) {
+      single_launch = false;
+      const int start = (int)plan.ranges.size();
+      int mx = 1, nb = 0;
+      for (auto& sg : segs) {
+        plan.ranges.push_back(RangeDesc{base + sg.first, base + sg.second, -1, 0});
+        mx = std::max(mx, sg.second - sg.first);
+        nb = std::max(nb, bufs_of(sg.first, sg.second));
+      }
+      plan.launches.push_back({start, (int)plan.ranges.size(), mx, nb});
+      const int tb = segs.back().second;
+      plan.ranges.push_back(RangeDesc{base + tb, base + n, li, 0});
+      plan.launches.push_back({(int)plan.ranges.size() - 1, (int)plan.ranges.size(), n - tb, bufs_of(tb, n)});
+    } else if (sched != SCHED_LEVELS) {
+      plan.ranges.push_back(RangeDesc{base, base + n, li, 0});
+    } else {
+      single_launch = false;
+      level_of.assign(n, 1);
+      int max_level = 1;
+      for (int j = 0; j < n; ++j) {
+        int lv = 1;
+        for (int kx = 0; kx < 2; ++kx)
+          if (kid[kx][j] >= 0) lv = std::max(lv, level_of[kid[kx][j]] + 1);
+        level_of[j] = lv;
+        max_level = std::max(max_level, lv);
+      }
+      by_level.resize(n);
+      for (int j = 0; j < n; ++j) by_level[j] = j;
+      std::stable_sort(by_level.begin(), by_level.end(), [&](int x, int y) { return level_of[x] < level_of[y]; });
+      int pos = 0;
+      for (int lv = 1; lv <= max_level; ++lv) {
+        const int start = (int)plan.ranges.size();
+        int nb = 0;
+        while (pos < n && level_of[by_level[pos]] == lv) {
+          const int j = by_level[pos++];   // order is the identity for this schedule
+          plan.ranges.push_back(RangeDesc{base + j, base + j + 1, (j == n - 1) ? li : -1, 0});
+          nb = std::max(nb, bufs_of(j, j + 1));
+        }
+        if ((int)plan.ranges.size() > start) plan.launches.push_back({start, (int)plan.ranges.size(), 1, nb});
+      }
+    }
+  }
+  if (single_launch) {
+    int mx = 0, nb = 0;
+    for (const RangeDesc& r : plan.ranges) mx = std::max(mx, r.end - r.begin);
+    for (const PlanOp& po : plan.ops) {
+      nb = std::max(nb, po.out_buf + 1);
+      for (int kx = 0; kx < 2; ++kx)
+        if (po.ch[kx].kind == SRC_STACK) nb = std::max(nb, po.ch[kx].ref + 1);
+    }
+    plan.launches.push_back({0, (int)plan.ranges.size(), mx, nb});
+  }
+  return 0;
+}
+
+// Releases what an evaluation acquired when it fails part-way (buffers and cherry records go back to their pools).
+struct EvalGuard {
+  cb_ctx* c;
+  std::vector<int> bufs, recs;
+  bool armed = true;
+  ~EvalGuard() {
+    if (!armed) return;
+    for (int b : bufs) buffer_release(c, b);
+    for (int r : recs) rec_release(c, r);
+  }
+};
+
+// Shared implementation of cb_eval (n_lists = 1) and cb_eval_batch.
 static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* offsets_in, const int32_t* nodes_in,
                      const int32_t* children_in, const int32_t* pslots_in, const double* pi, int flags,
                      int* snapshot_out, double* lnl_out) {
   REQUIRE(c && c->n_states > 0, "cb_set_tips must come first");
   REQUIRE(offsets_in && nodes_in && children_in && pslots_in && pi, "null argument");
   REQUIRE(snapshot_in < 0 || snapshot_valid(c, snapshot_in), "invalid snapshot %d", snapshot_in);
-  const int C = c->n_cats, N = c->n_taxa, n_nodes = 2 * N;  // ids 1 .. 2N-1
-  REQUIRE(offsets_in[n_lists] > 0, "empty op list");
-
-  // ---- cherry folding (2-state family) ---------------------------------------------------------
-  // An op whose two children are tips is not run: its parent (which is always in the list) takes it
-  // as a SRC_CHERRY child and looks the cherry's 3 x 3 possible partials up.  The compacted op list
-  // replaces the caller's; fold_child remembers, per (compacted op, child), the caller's op index
-  // of the folded cherry.
-  std::vector<int32_t> offsets_v(offsets_in, offsets_in + n_lists + 1), nodes_v, children_v, pslots_v, fold_child;
-  const bool fold = c->family_s2 && !(flags & CB_EVAL_NO_FOLD);
-  if (fold) {
-    std::vector<int32_t> parent_op(n_nodes);
-    for (int li = 0; li < n_lists; ++li) {
-      const int b = offsets_in[li], e = offsets_in[li + 1];
-      std::fill(parent_op.begin(), parent_op.end(), -1);
-      for (int i = b; i < e; ++i)
-        for (int kx = 0; kx < 2; ++kx) {
-          const int ch = children_in[2 * i + kx];
-          if (ch > N && ch < n_nodes) parent_op[ch] = i;
-        }
-      offsets_v[li] = (int32_t)nodes_v.size();
-      std::vector<int32_t> folded_at(n_nodes, -1);  // node -> caller's op index of its folded cherry op
-      for (int i = b; i < e; ++i) {
-        const int node = nodes_in[i], c0 = children_in[2 * i], c1 = children_in[2 * i + 1];
-        const bool cherry = c0 >= 1 && c0 <= N && c1 >= 1 && c1 <= N && i != e - 1 && node > N && node < n_nodes &&
-                            parent_op[node] > i;
-        if (cherry) {
-          folded_at[node] = i;
-          continue;
-        }
-        nodes_v.push_back(node);
-        for (int kx = 0; kx < 2; ++kx) {
-          const int ch = children_in[2 * i + kx];
-          children_v.push_back(ch);
-          fold_child.push_back((ch > N && ch < n_nodes) ? folded_at[ch] : -1);
-          for (int q = 0; q < C; ++q) pslots_v.push_back(pslots_in[(size_t)(2 * i + kx) * C + q]);
-        }
-      }
-    }
-    offsets_v[n_lists] = (int32_t)nodes_v.size();
-  }
-  const int32_t* offsets = fold ? offsets_v.data() : offsets_in;
-  const int32_t* nodes = fold ? nodes_v.data() : nodes_in;
-  const int32_t* children = fold ? children_v.data() : children_in;
-  const int32_t* pslots = fold ? pslots_v.data() : pslots_in;
-  const int total_ops = offsets[n_lists];
-  REQUIRE(total_ops > 0, "empty op list");
-  std::vector<int> new_cherry_nodes, new_cherry_recs;  // folded cherries that stay in the returned snapshot
+  const int C = c->n_cats, N = c->n_taxa, n_nodes = 2 * N;
+  REQUIRE(n_lists >= 1 && offsets_in[0] == 0 && offsets_in[n_lists] > 0, "empty op list");
+  const int total_in = offsets_in[n_lists];
   const bool want_snap = (flags & CB_EVAL_WANT_SNAPSHOT) != 0;
-  const bool store_root = (flags & CB_EVAL_STORE_ROOT) != 0;
   REQUIRE(!(want_snap && n_lists != 1), "snapshots are only kept for single evaluations");
   CU(cudaSetDevice(c->device));
-  if (ensure_staging(c, total_ops, total_ops + n_lists, n_lists)) return 1;
+
+  // ---- the plan: cached per (op list, flags) for full evaluations, built on the spot for dirty paths
+  const int split_env = getenv("CYBAYES_WALK_SPLIT") ? atoi(getenv("CYBAYES_WALK_SPLIT")) : 0;
+  EvalPlan* plan = nullptr;
+  if (snapshot_in < 0 && !c->no_plan_cache) {
+    for (auto& p : c->plans)
+      if (p.n_lists == n_lists && p.flags == (flags & PLAN_FLAG_MASK) && p.split_env == split_env &&
+          (int)p.key_nodes.size() == total_in && memcmp(p.key_offsets.data(), offsets_in, (size_t)(n_lists + 1) * 4) == 0 &&
+          memcmp(p.key_nodes.data(), nodes_in, (size_t)total_in * 4) == 0 &&
+          memcmp(p.key_children.data(), children_in, (size_t)total_in * 8) == 0) {
+        plan = &p;
+        break;
+      }
+    if (!plan) {
+      if ((int)c->plans.size() < PLAN_CACHE_SIZE) {
+        c->plans.emplace_back();
+        plan = &c->plans.back();
+      } else {  // evict the least recently used
+        plan = &c->plans[0];
+        for (auto& p : c->plans)
+          if (p.stamp < plan->stamp) plan = &p;
+      }
+      plan->n_lists = 0;  // invalid while it is rebuilt
+      plan->split_env = split_env;
+      if (build_plan(c, nullptr, n_lists, offsets_in, nodes_in, children_in, flags, *plan)) { plan->key_nodes.clear(); return 1; }
+      plan->n_lists = n_lists;
+      plan->flags = flags & PLAN_FLAG_MASK;
+      plan->key_offsets.assign(offsets_in, offsets_in + n_lists + 1);
+      plan->key_nodes.assign(nodes_in, nodes_in + total_in);
+      plan->key_children.assign(children_in, children_in + 2 * (size_t)total_in);
+      c->plan_builds++;
+    }
+    plan->stamp = ++c->plan_clock;
+  } else {
+    plan = &c->scratch_plan;
+    plan->split_env = split_env;
+    if (build_plan(c, snapshot_in >= 0 ? &c->snaps[snapshot_in] : nullptr, n_lists, offsets_in, nodes_in, children_in, flags, *plan))
+      return 1;
+    c->plan_builds++;
+  }
+  const int total_ops = (int)plan->ops.size();
+  const int n_ranges = (int)plan->ranges.size();
+
+  // every P slot the ops name, before anything is acquired
+  for (size_t i = 0; i < (size_t)total_in * 2 * C; ++i)
+    REQUIRE(pslots_in[i] >= 0 && pslots_in[i] < c->pmat_cap, "P slot %d out of range (reserved %d)", pslots_in[i], c->pmat_cap);
+
+  if (ensure_staging(c, total_ops, n_ranges, n_lists)) return 1;
   CU(cudaEventSynchronize(c->ev_stage));  // previous H2D of the staging area finished
 
+  // ---- fill the descriptors: buffers, pointers, P slots
   const Snapshot* sin = snapshot_in >= 0 ? &c->snaps[snapshot_in] : nullptr;
-  c->op_of_node.assign(n_nodes, -1);
-  std::vector<int> new_bufs, new_nodes;  // buffers written by this evaluation, and their nodes
-  std::vector<int> tmp_bufs;             // temporaries of an evaluation that keeps no snapshot
-  int n_ranges = 0;
-  std::vector<std::pair<int, int>> launches;  // [range begin, range end) per launch
-  std::vector<int> launch_maxops;
-  bool single_launch = true;
-  std::vector<int>& order = c->order;    // position -> original op index (per list)
-  std::vector<int> pos_of, n_sub, kid_op[2], range_id;
-  std::vector<std::pair<int, int>> walk_segs;
-  std::vector<char> read_back;
-
-  for (int li = 0; li < n_lists; ++li) {
-    const int b = offsets[li], e = offsets[li + 1], n = e - b;
-    REQUIRE(n > 0, "empty op list %d", li);
-    for (int i = b; i < e; ++i) {
-      const int node = nodes[i];
-      REQUIRE(node > N && node < n_nodes, "op %d: node %d is not an internal node", i, node);
-      REQUIRE(c->op_of_node[node] < 0, "op %d: node %d is computed twice", i, node);
-      c->op_of_node[node] = i;
-    }
-    // producers of the children inside this list (-1: tip or snapshot)
-    kid_op[0].assign(n, -1);
-    kid_op[1].assign(n, -1);
-    for (int i = b; i < e; ++i)
-      for (int kx = 0; kx < 2; ++kx) {
-        const int ch = children[2 * i + kx];
-        REQUIRE((ch >= 1 && ch <= N) || (ch > N && ch < n_nodes), "op %d: bad child id %d", i, ch);
-        if (ch > N && c->op_of_node[ch] >= b) {
-          REQUIRE(c->op_of_node[ch] < i, "op %d: child %d is computed after its parent", i, ch);
-          kid_op[kx][i - b] = c->op_of_node[ch] - b;
-        }
+  EvalGuard guard{c};
+  std::vector<int>& new_bufs = c->work_new_bufs;
+  std::vector<int>& new_nodes = c->work_new_nodes;
+  std::vector<int>& new_cherry_nodes = c->work_cherry_nodes;
+  new_bufs.clear(); new_nodes.clear(); new_cherry_nodes.clear();
+  const char* codes = (const char*)c->d_codes;
+  const size_t row_bytes = (size_t)c->P * c->code_bytes;
+  for (int p = 0; p < total_ops; ++p) {
+    const PlanOp& po = plan->ops[p];
+    OpDesc& op = c->h_ops[p];
+    op.is_root = po.is_root;
+    op.pad_ = po.stream;
+    op.spill = po.spill;
+    op.out_buf = po.out_buf;
+    op.dst = nullptr;
+    op.dst_scale = nullptr;
+    if (po.keep) {
+      int bi;
+      if (buffer_acquire(c, &bi)) return 1;
+      guard.bufs.push_back(bi);
+      op.dst = c->buffers[bi].data;
+      op.dst_scale = c->buffers[bi].scale;
+      if (want_snap) {
+        new_bufs.push_back(bi);
+        new_nodes.push_back(po.node);
       }
-    // chain: every op after the first consumes exactly the previous op and nothing else of the list
-    bool chain = !(flags & CB_EVAL_FORCE_LEVELS) && n <= MAX_CHAIN_OPS;
-    for (int i = 0; i < n && chain; ++i) {
-      const int a0 = kid_op[0][i], a1 = kid_op[1][i];
-      if (i == 0) chain = (a0 < 0 && a1 < 0);
-      else chain = (a0 == i - 1) != (a1 == i - 1) && (a0 < 0 || a0 == i - 1) && (a1 < 0 || a1 == i - 1);
     }
-    REQUIRE(chain || n_lists == 1, "cb_eval_batch: candidate %d is not a chain of at most %d ops", li, MAX_CHAIN_OPS);
-    Schedule sched = SCHED_CHAIN;
-    if (!chain) {
-      // the register-carried kernel only pays off when the partial is carried: its alignments always walk
-      const bool big = c->dmma_rc || c->P >= (c->family_s2 ? WALK_MIN_SITES_S2 : WALK_MIN_SITES_GENERAL);
-      sched = ((big || (flags & CB_EVAL_FORCE_WALK)) && !(flags & CB_EVAL_FORCE_LEVELS)) ? SCHED_WALK : SCHED_LEVELS;
-    }
-
-    order.resize(n);
-    for (int i = 0; i < n; ++i) order[i] = i;
-    if (sched == SCHED_WALK) {
-      // subtree sizes in ops (children precede parents in the caller's order)
-      n_sub.assign(n, 1);
-      for (int i = 0; i < n; ++i)
-        for (int kx = 0; kx < 2; ++kx)
-          if (kid_op[kx][i] >= 0) n_sub[i] += n_sub[kid_op[kx][i]];
-      // Post-order from the root op, heavier child subtree first.  When the alignment gives too few
-      // site tiles to fill the GPU for a whole sequential walk (small shards), the tree is cut into
-      // independent subtrees of at most `limit` ops that run as parallel ranges of a first launch;
-      // the ops above the cut follow in a second launch.
-      int limit = n + 1;
-      {
-        const int64_t tile_sites = c->family_s2 ? (int64_t)256 * c->s2_vec : (c->dmma_rc ? RC_T : (c->use_dmma ? DM_T : GEN_T));
-        const int64_t blocks = (c->P + tile_sites - 1) / tile_sites * (c->family_s2 ? 1 : c->n_cats);
-        const int64_t slots = (int64_t)c->sm_count * (c->family_s2 ? (c->s2_vec == 1 ? 3 : 2) : (c->dmma_rc ? 1 : 2));
-        if (blocks < 4 * slots && n >= 64 && !(flags & CB_EVAL_FORCE_WALK))
-          limit = std::max(16, std::min(256, (int)(n * blocks / (8 * slots)) + 1));
-        if (getenv("CYBAYES_WALK_SPLIT")) limit = std::max(2, atoi(getenv("CYBAYES_WALK_SPLIT")));
-        if (limit >= n) limit = n + 1;  // nothing to cut
-      }
-      std::vector<int> out, top, stack;
-      std::vector<char> expanded(n, 0);
-      std::vector<std::pair<int, int>> segs;
-      out.reserve(n);
-      auto post_order = [&](int root_op) {
-        stack.clear();
-        stack.push_back(root_op);
-        while (!stack.empty()) {
-          const int i = stack.back();
-          if (expanded[i]) {
-            stack.pop_back();
-            out.push_back(i);
-            continue;
+    for (int kx = 0; kx < 2; ++kx) {
+      const PlanChild& pc = po.ch[kx];
+      op.kind[kx] = pc.kind;
+      op.src[kx] = nullptr;
+      op.src_scale[kx] = nullptr;
+      op.ctip[kx][0] = op.ctip[kx][1] = nullptr;
+      op.crec_out[kx] = -1;
+      op.in_buf[kx] = -1;
+      const int32_t* ps = pslots_in + (size_t)pc.edge * C;
+      for (int q = 0; q < C; ++q) op.pslot[kx][q] = ps[q];
+      for (int q = C; q < CB_MAX_CATS; ++q) op.pslot[kx][q] = 0;
+      switch (pc.kind) {
+        case SRC_TIP:
+          op.src[kx] = codes + (size_t)(pc.ref - 1) * row_bytes;
+          break;
+        case SRC_BUFFER:
+          if (pc.ref >= 0) {
+            op.src[kx] = c->h_ops[pc.ref].dst;
+            op.src_scale[kx] = c->h_ops[pc.ref].dst_scale;
+          } else {
+            const Buffer& bf = c->buffers[sin->buf_of_node[~pc.ref]];
+            op.src[kx] = bf.data;
+            op.src_scale[kx] = bf.scale;
           }
-          expanded[i] = 1;
-          int a0 = kid_op[0][i], a1 = kid_op[1][i];
-          if (a0 >= 0 && a1 >= 0 && n_sub[a1] > n_sub[a0]) std::swap(a0, a1);  // a0 = heavier
-          if (a1 >= 0) stack.push_back(a1);  // lighter: visited second (pushed first)
-          if (a0 >= 0) stack.push_back(a0);
-        }
-      };
-      if (limit > n) {
-        post_order(n - 1);
-      } else {
-        // walk down from the root: ops with a subtree above the limit stay in `top`
-        std::vector<std::pair<int, int>> st2;  // (op, phase)
-        std::vector<int> cut;
-        st2.push_back({n - 1, 0});
-        while (!st2.empty()) {
-          auto [i, phase] = st2.back();
-          st2.pop_back();
-          if (phase == 1) { top.push_back(i); continue; }
-          if (n_sub[i] <= limit) { cut.push_back(i); continue; }
-          st2.push_back({i, 1});
-          int a0 = kid_op[0][i], a1 = kid_op[1][i];
-          if (a0 >= 0 && a1 >= 0 && n_sub[a1] > n_sub[a0]) std::swap(a0, a1);
-          if (a1 >= 0) st2.push_back({a1, 0});
-          if (a0 >= 0) st2.push_back({a0, 0});
-        }
-        std::stable_sort(cut.begin(), cut.end(), [&](int x, int y) { return n_sub[x] > n_sub[y]; });  // big first
-        for (int r : cut) {
-          const int b0 = (int)out.size();
-          post_order(r);
-          segs.push_back({b0, (int)out.size()});
-        }
-        for (int i : top) out.push_back(i);
-      }
-      if ((int)out.size() == n) {
-        order = out;
-        range_id.assign(n, 0);
-        for (size_t si = 0; si < segs.size(); ++si)
-          for (int p = segs[si].first; p < segs[si].second; ++p) range_id[p] = (int)si + 1;
-        walk_segs = segs;
-      } else {
-        sched = SCHED_LEVELS;  // ops not under the root
-      }
-    }
-    if (sched != SCHED_WALK) { range_id.assign(n, 0); walk_segs.clear(); }
-    pos_of.assign(n, 0);
-    for (int p = 0; p < n; ++p) pos_of[order[p]] = p;
-    // which ops are read back from memory by a later op (as opposed to carried on chip)?
-    read_back.assign(n, 0);
-    for (int i = 0; i < n; ++i)
-      for (int kx = 0; kx < 2; ++kx) {
-        const int k0 = kid_op[kx][i];
-        if (k0 >= 0 && !(sched != SCHED_LEVELS && pos_of[k0] == pos_of[i] - 1 && range_id[pos_of[k0]] == range_id[pos_of[i]]))
-          read_back[k0] = 1;
-      }
-
-    for (int p = 0; p < n; ++p) {
-      const int i0 = order[p], i = b + i0;
-      OpDesc& op = c->h_ops[b + p];
-      const bool is_root = (i0 == n - 1);
-      REQUIRE(!is_root || p == n - 1, "internal error: root is not last");
-      op.is_root = is_root ? 1 : 0;
-      op.pad_ = (read_back[i0] || !c->s2_stream_stores) ? 0 : 1;  // 1: nobody reads this partial back in this evaluation -> streaming stores
-      op.dst = nullptr;
-      op.dst_scale = nullptr;
-      const bool keep = is_root ? (want_snap && store_root) : (want_snap || read_back[i0]);
-      if (keep) {
-        int bi;
-        if (buffer_acquire(c, &bi)) return 1;
-        op.dst = c->buffers[bi].data;
-        op.dst_scale = c->buffers[bi].scale;
-        if (want_snap) {
-          new_bufs.push_back(bi);
-          new_nodes.push_back(nodes[i]);
-        } else {
-          tmp_bufs.push_back(bi);
-        }
-      }
-      for (int kx = 0; kx < 2; ++kx) {
-        const int ch = children[2 * i + kx];
-        op.src[kx] = nullptr;
-        op.src_scale[kx] = nullptr;
-        op.ctip[kx][0] = op.ctip[kx][1] = nullptr;
-        op.crec_out[kx] = -1;
-        for (int t = 0; t < 2; ++t)
-          for (int q = 0; q < CB_S2_MAX_CATS; ++q) op.cslot[kx][t][q] = 0;
-        const int folded = fold ? fold_child[(size_t)2 * i + kx] : -1;
-        const int snap_rec = (fold && folded < 0 && ch > N && kid_op[kx][i0] < 0 && sin &&
-                              ch < (int)sin->cherry_of_node.size()) ? sin->cherry_of_node[ch] : -1;
-        if (ch <= N) {
-          op.kind[kx] = SRC_TIP;
-          op.src[kx] = (const char*)c->d_codes + (size_t)(ch - 1) * c->P * c->code_bytes;
-        } else if (folded >= 0) {
-          // the cherry was in the caller's list: its P matrices are the caller's slots
-          op.kind[kx] = SRC_CHERRY;
-          for (int t = 0; t < 2; ++t) {
-            const int tip = children_in[2 * folded + t];
-            op.ctip[kx][t] = (const char*)c->d_codes + (size_t)(tip - 1) * c->P * c->code_bytes;
-            for (int q = 0; q < C; ++q) {
-              const int sl = pslots_in[(size_t)(2 * folded + t) * C + q];
-              REQUIRE(sl >= 0 && sl < c->pmat_cap, "op %d: P slot %d out of range", folded, sl);
-              op.cslot[kx][t][q] = sl;
+          break;
+        case SRC_STACK:
+          op.in_buf[kx] = pc.ref;
+          break;
+        case SRC_CHERRY:
+          if (pc.ref >= 0) {  // folded out of the caller's list: its P matrices are the caller's slots
+            const int fo = pc.ref;
+            for (int t = 0; t < 2; ++t) {
+              const int tip = children_in[2 * fo + t];
+              op.ctip[kx][t] = codes + (size_t)(tip - 1) * row_bytes;
+              const int32_t* cs = pslots_in + (size_t)(2 * fo + t) * C;
+              for (int q = 0; q < CB_S2_MAX_CATS; ++q) op.cslot[kx][t][q] = q < C ? cs[q] : 0;
+            }
+            if (want_snap) {
+              int r;
+              if (rec_acquire(c, children_in[2 * fo], children_in[2 * fo + 1], &r)) return 1;
+              guard.recs.push_back(r);
+              op.crec_out[kx] = r;
+              new_cherry_nodes.push_back(nodes_in[fo]);
+            }
+          } else {            // kept by the input snapshot: its P matrices live in the library's pool
+            const int rec = sin->cherry_of_node[~pc.ref];
+            for (int t = 0; t < 2; ++t) {
+              op.ctip[kx][t] = codes + (size_t)(c->recs[rec].tip[t] - 1) * row_bytes;
+              for (int q = 0; q < CB_S2_MAX_CATS; ++q) op.cslot[kx][t][q] = q < C ? (CB_LIB_SLOT | (rec * 2 * C + t * C + q)) : 0;
             }
           }
-          if (want_snap) {
-            int r;
-            if (rec_acquire(c, children_in[2 * folded], children_in[2 * folded + 1], &r)) return 1;
-            op.crec_out[kx] = r;
-            new_cherry_nodes.push_back(ch);
-            new_cherry_recs.push_back(r);
-          }
-        } else if (snap_rec >= 0) {
-          // a cherry kept by the input snapshot: its P matrices live in the library's pool
-          op.kind[kx] = SRC_CHERRY;
-          for (int t = 0; t < 2; ++t) {
-            op.ctip[kx][t] = (const char*)c->d_codes + (size_t)(c->recs[snap_rec].tip[t] - 1) * c->P * c->code_bytes;
-            for (int q = 0; q < C; ++q) op.cslot[kx][t][q] = CB_LIB_SLOT | (snap_rec * 2 * C + t * C + q);
-          }
-        } else if (kid_op[kx][i0] >= 0) {
-          const int pp = pos_of[kid_op[kx][i0]];
-          if (sched != SCHED_LEVELS && pp == p - 1 && range_id[pp] == range_id[p]) {
-            op.kind[kx] = SRC_CARRIED;
-          } else {
-            const OpDesc& prod = c->h_ops[b + pp];
-            REQUIRE(pp < p && prod.dst, "internal error: producer of node %d has no buffer", ch);
-            op.kind[kx] = SRC_BUFFER;
-            op.src[kx] = prod.dst;
-            op.src_scale[kx] = prod.dst_scale;
-          }
-        } else {
-          REQUIRE(sin && ch < (int)sin->buf_of_node.size() && sin->buf_of_node[ch] >= 0,
-                  "op %d: child %d is neither recomputed nor in the input snapshot", i, ch);
-          const Buffer& bf = c->buffers[sin->buf_of_node[ch]];
-          op.kind[kx] = SRC_BUFFER;
-          op.src[kx] = bf.data;
-          op.src_scale[kx] = bf.scale;
-        }
-        for (int q = 0; q < C; ++q) {
-          const int sl = pslots[(size_t)(2 * i + kx) * C + q];
-          REQUIRE(sl >= 0 && sl < c->pmat_cap, "op %d: P slot %d out of range", i, sl);
-          op.pslot[kx][q] = sl;
-        }
-        for (int q = C; q < CB_MAX_CATS; ++q) op.pslot[kx][q] = 0;
+          break;
+        default: break;
       }
     }
-
-    if (sched == SCHED_WALK && !walk_segs.empty()) {
-      single_launch = false;
-      const int start = n_ranges;
-      int mx = 1;
-      for (auto& sg : walk_segs) {
-        RangeDesc& r = c->h_ranges[n_ranges++];
-        r.begin = b + sg.first; r.end = b + sg.second; r.out_index = -1; r.pad_ = 0;
-        mx = std::max(mx, sg.second - sg.first);
-      }
-      launches.push_back({start, n_ranges});
-      launch_maxops.push_back(mx);
-      RangeDesc& r = c->h_ranges[n_ranges++];
-      r.begin = b + walk_segs.back().second; r.end = e; r.out_index = li; r.pad_ = 0;
-      launches.push_back({n_ranges - 1, n_ranges});
-      launch_maxops.push_back(r.end - r.begin);
-    } else if (sched != SCHED_LEVELS) {
-      RangeDesc& r = c->h_ranges[n_ranges++];
-      r.begin = b; r.end = e; r.out_index = li; r.pad_ = 0;
-    } else {
-      single_launch = false;
-      c->level_of_op.assign(n, 1);
-      int max_level = 1;
-      for (int i = 0; i < n; ++i) {
-        int lv = 1;
-        for (int kx = 0; kx < 2; ++kx)
-          if (kid_op[kx][i] >= 0) lv = std::max(lv, c->level_of_op[kid_op[kx][i]] + 1);
-        c->level_of_op[i] = lv;
-        max_level = std::max(max_level, lv);
-      }
-      std::vector<int> by_level(n);
-      for (int i = 0; i < n; ++i) by_level[i] = i;
-      std::stable_sort(by_level.begin(), by_level.end(),
-                       [&](int x, int y) { return c->level_of_op[x] < c->level_of_op[y]; });
-      int pos = 0;
-      for (int lv = 1; lv <= max_level; ++lv) {
-        const int start = n_ranges;
-        while (pos < n && c->level_of_op[by_level[pos]] == lv) {
-          const int i = b + by_level[pos++];
-          RangeDesc& r = c->h_ranges[n_ranges++];
-          r.begin = i; r.end = i + 1; r.out_index = (i == e - 1) ? li : -1; r.pad_ = 0;
-        }
-        if (n_ranges > start) {
-          launches.push_back({start, n_ranges});
-          launch_maxops.push_back(1);
-        }
-      }
-    }
-    for (int i = b; i < e; ++i) c->op_of_node[nodes[i]] = -1;
   }
-  if (single_launch) {
-    int mx = 0;
-    for (int li = 0; li < n_lists; ++li) mx = std::max(mx, offsets[li + 1] - offsets[li]);
-    launches.push_back({0, n_ranges});
-    launch_maxops.push_back(mx);
-  }
+  memcpy(c->h_ranges, plan->ranges.data(), (size_t)n_ranges * sizeof(RangeDesc));
 
   if (ensure_lib_pool(c)) return 1;
   // upload descriptors + pi, launch
@@ -1206,8 +1489,11 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     CU(cudaGetLastError());
     c->launches += 1;
   }
-  for (size_t li = 0; li < launches.size(); ++li)
-    if (launch_ranges(c, k, launches[li].first, launches[li].second, launch_maxops[li])) return 1;
+  if (launch_images(c, k, total_ops)) return 1;
+  CU(cudaEventRecord(c->ev_main0, c->stream));
+  for (const PlanLaunch& pl : plan->launches)
+    if (launch_ranges(c, k, pl.r_begin, pl.r_end, pl.max_ops, pl.n_bufs)) return 1;
+  CU(cudaEventRecord(c->ev_main1, c->stream));
   if (!c->family_s2) {
     dim3 grid((unsigned)((c->P + 255) / 256), (unsigned)n_lists);
     root_combine_kernel<<<grid, 256, 0, c->stream>>>(k);
@@ -1216,6 +1502,11 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   }
   CU(cudaEventRecord(c->ev1, c->stream));
   c->timing_valid = true;
+  c->last_bytes_written = plan->bytes_written;
+  c->last_bytes_read = plan->bytes_read;
+  c->last_counts[0] = total_ops; c->last_counts[1] = plan->n_stored; c->last_counts[2] = plan->n_buffer_reads;
+  c->last_counts[3] = plan->n_stack; c->last_counts[4] = plan->n_spills; c->last_counts[5] = plan->n_cherries;
+  c->last_counts[6] = (int)plan->launches.size(); c->last_counts[7] = (int)c->plan_builds;
 
   if (c->comm) {
     int r = g_nccl.AllReduce(c->d_results, c->d_results, (size_t)n_lists, NCCL_DOUBLE, NCCL_SUM, c->comm, c->stream);
@@ -1226,7 +1517,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   c->last_n_out = n_lists;
 
   // bookkeeping (stream-ordered: temporaries may be recycled by later launches on this stream)
-  for (int bi : tmp_bufs) buffer_release(c, bi);
+  guard.armed = false;
   if (want_snap) {
     int sid;
     if (!c->free_snaps.empty()) {
@@ -1258,11 +1549,12 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
       else if (bi <= -2) bi = new_bufs[-2 - bi];  // ownership moves from this evaluation to the snapshot
       int32_t& ri = sn.cherry_of_node[nd];
       if (ri >= 0) c->recs[ri].refs++;
-      else if (ri <= -2) ri = new_cherry_recs[-2 - ri];
+      else if (ri <= -2) ri = guard.recs[-2 - ri];
     }
     if (snapshot_out) *snapshot_out = sid;
-  } else if (snapshot_out) {
-    *snapshot_out = -1;
+  } else {
+    for (int bi : guard.bufs) buffer_release(c, bi);   // temporaries of an evaluation that keeps no snapshot
+    if (snapshot_out) *snapshot_out = -1;
   }
 
   if (!(flags & CB_EVAL_NO_SYNC)) {
@@ -1306,6 +1598,20 @@ extern "C" int cb_last_eval_ms(cb_ctx* c, float* ms) {
   CU(cudaSetDevice(c->device));
   CU(cudaEventSynchronize(c->ev1));
   CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return 0;
+}
+extern "C" int cb_last_eval_main_ms(cb_ctx* c, float* ms) {
+  REQUIRE(c && ms && c->timing_valid, "no evaluation has been timed");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->ev_main1));
+  CU(cudaEventElapsedTime(ms, c->ev_main0, c->ev_main1));
+  return 0;
+}
+extern "C" int cb_last_eval_info(cb_ctx* c, int64_t* bytes_written, int64_t* bytes_read, int32_t* counts8) {
+  REQUIRE(c && c->timing_valid, "no evaluation has run");
+  if (bytes_written) *bytes_written = c->last_bytes_written;
+  if (bytes_read) *bytes_read = c->last_bytes_read;
+  if (counts8) memcpy(counts8, c->last_counts, sizeof c->last_counts);
   return 0;
 }
 extern "C" int cb_mark(cb_ctx* c, int which) {

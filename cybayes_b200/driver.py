@@ -84,6 +84,21 @@ def _spr_dirty_nodes(old_parent_of, new_tree, root):
     return out
 
 
+def spr_tables(tmats, tree_prop, pi, rates, site_rates):
+    """Per-category P tables of the tree after an external SPR: the tables of the current tree with the three
+    removed edges dropped and the three new ones built (same matrices as a full get_prob_t would give them)."""
+    out = []
+    for k, rate in enumerate(site_rates):
+        t = tmats[k].copy()
+        for e in [e for e in t.keys() if e not in tree_prop]:
+            del t[e]
+        for e, bl in tree_prop.items():
+            if e not in t:
+                t[e] = get_edge_transition_mat(pi, rates, bl * rate)
+        out.append(t)
+    return out
+
+
 def run_chain(input_file, model, n_gen, thin, data_type, output_file, reader=None, seed=1234,
               out=sys.stdout, fast_spr=False, on_generation=None, diag=None):
     """Run the chain; returns a dict with the final state, counters and timings.  `diag` (a dict) receives, before
@@ -189,15 +204,7 @@ def run_chain(input_file, model, n_gen, thin, data_type, output_file, reader=Non
                                                       n_sites, n_taxa, n_cats)
         elif name == "externalSPR" and fast_spr:
             dirty_set = _spr_dirty_nodes(parent_of, tree_prop, root)
-            prop_tmats = []
-            for k, rate in enumerate(site_rates):
-                t = tmats[k].copy()
-                for e in [e for e in t.keys() if e not in tree_prop]:
-                    del t[e]
-                for e, bl in tree_prop.items():
-                    if e not in t:
-                        t[e] = get_edge_transition_mat(pi_prop, rates_prop, bl * rate)
-                prop_tmats.append(t)
+            prop_tmats = spr_tables(tmats, tree_prop, pi_prop, rates_prop, site_rates)
             if dirty_set:
                 proposed_ll, proposed_cache = cache_matML(pi_prop, root, leaves, cache, list(dirty_set), order_prop,
                                                           prop_tmats, n_sites, n_taxa, n_cats)

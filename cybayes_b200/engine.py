@@ -223,6 +223,22 @@ class Engine(SlotPool):
         check(self._lib.cb_last_eval_ms(self._ctx, C.byref(ms)))
         return float(ms.value)
 
+    def last_eval_main_ms(self):
+        """Device time of the pruning launches alone (no P-layout / op-image pre-pass)."""
+        ms = C.c_float()
+        check(self._lib.cb_last_eval_main_ms(self._ctx, C.byref(ms)))
+        return float(ms.value)
+
+    def last_eval_info(self):
+        """What the last evaluation had to move (bytes, from its op list) and how it was scheduled."""
+        w, r = C.c_int64(), C.c_int64()
+        counts = np.zeros(8, dtype=np.int32)
+        check(self._lib.cb_last_eval_info(self._ctx, C.byref(w), C.byref(r), _i32(counts)))
+        names = ("ops", "stored", "read_back", "stack_pops", "spills", "cherries_folded", "launches", "plans_built")
+        out = dict(zip(names, (int(x) for x in counts)))
+        out["bytes_written"], out["bytes_read"] = w.value, r.value
+        return out
+
     def mark(self, which):
         check(self._lib.cb_mark(self._ctx, int(which)))
 

@@ -106,8 +106,10 @@ int cb_pmat_build(cb_ctx* ctx, int model, const double* pi, double beta, const d
 int cb_eval(cb_ctx* ctx, int snapshot_in, int n_ops, const int32_t* nodes,
             const int32_t* children, const int32_t* pslots, const double* pi, int flags,
             int* snapshot_out, double* lnl_out);
-/* n_batch independent candidate op lists against the same snapshot; each list must be a
- * chain (every op after the first consumes the previous op's node).  No snapshot is kept. */
+/* n_batch independent candidate op lists against the same snapshot, ONE launch (grid.y = candidates).  A
+ * candidate is usually a chain (a dirty path: every op after the first consumes the previous op's node); any
+ * list whose ops all lie under its last op is accepted (two paths that merge -- an external SPR,
+ * mcmc_gamma.pyx:136-185 -- or a whole tree) and walked depth-first.  No snapshot is kept. */
 int cb_eval_batch(cb_ctx* ctx, int snapshot_in, int n_batch, const int32_t* op_offsets,
                   const int32_t* nodes, const int32_t* children, const int32_t* pslots,
                   const double* pi, double* lnl_out);
@@ -125,6 +127,13 @@ int cb_stats(cb_ctx* ctx, int64_t* kernel_launches, int64_t* bytes_h2d, int64_t*
 /* device time in ms of the kernels of the last synchronous cb_eval / cb_eval_batch
  * (CUDA events on the launching stream) */
 int cb_last_eval_ms(cb_ctx* ctx, float* ms_out);
+/* ... of its pruning launches alone (without the per-evaluation pre-pass that lays out P matrices / op images) */
+int cb_last_eval_main_ms(cb_ctx* ctx, float* ms_out);
+/* What the last evaluation had to move, from its op list: bytes of partials (+ exponents) it stored, bytes it
+ * read (stored partials read back, tip codes, pattern weights) -- the roofline numerator of bench.py -- and
+ * counts8 = { ops run, partials stored, partials read back, children popped from the shared-memory stack,
+ * partials stored and re-read inside one launch, cherries folded, pruning launches, plans built so far }. */
+int cb_last_eval_info(cb_ctx* ctx, int64_t* bytes_written, int64_t* bytes_read, int32_t* counts8);
 /* CUDA events on the engine's stream: cb_mark(ctx, 0) ... work ... cb_mark(ctx, 1); elapsed = device ms */
 int cb_mark(cb_ctx* ctx, int which);
 int cb_mark_elapsed_ms(cb_ctx* ctx, float* ms_out);

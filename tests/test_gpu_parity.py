@@ -187,8 +187,8 @@ def _check_random_inputs(S, n_taxa, n_sites, model, **problem):
         pi = np.full(S, 1.0 / S)
         beta = oracle.f81_beta(pi)
     tm = [oracle.prob_t(model, False, pi, tree, er, r, beta=beta) for r in rates]
-    want, want_cache = oracle.mat_ml(pi, root, leaves, edges, tm, n_sites, n_taxa)
-    want_scaled = oracle.mat_ml_scaled(pi, root, leaves, edges, tm, n_sites, n_taxa)
+    want, want_cache = oracle.mat_ml(pi, root, leaves, edges, tm, n_sites, n_taxa, n_cats=C)
+    want_scaled = oracle.mat_ml_scaled(pi, root, leaves, edges, tm, n_sites, n_taxa, n_cats=C)
     assert abs(want - want_scaled) <= 1e-13 * abs(want)
 
     eng = Engine(codes, S, C, amb)
@@ -571,3 +571,86 @@ def test_c1_at_its_stated_length_unmodified_script(gpu_backend, tmp_path, monkey
     assert hashlib.sha256(open(str(tmp_path / "c1ref.trees")).read().encode()).hexdigest() == meta["trees_sha256"]
     counters = [l for l in out.splitlines() if l.startswith("(np.str_(") or l.startswith("('")]
     assert sorted(counters) == sorted(meta["counters"])
+
+
+@pytest.mark.parametrize("n_taxa,n_sites,model,slots,n_cats", [(2, 70, "F81", 3, 4), (12, 333, "F81", 3, 4),
+                                                               (40, 1000, "GTR", 1, 4), (64, 3000, "GTR", 0, 4),
+                                                               (33, 257, "F81", 2, 4), (200, 640, "GTR", 3, 4),
+                                                               (25, 500, "F81", 3, 1), (90, 2100, "GTR", 2, 1)])
+def test_tiled_two_state_kernel_small_inputs(n_taxa, n_sites, model, slots, n_cats, gpu_backend, monkeypatch):
+    """The large-alignment 2-state kernel (kernels_s2t.cuh: tile-interleaved partials, shared-memory stack, bulk-async
+    stores, op images) forced onto small inputs: ragged last blocks, 0-3 stack slots (spills through global memory),
+    every schedule, dirty paths and batches -- and bit-identical partials to the row-major kernel."""
+    from cybayes_b200.engine import Engine
+    from cybayes_b200.likelihood import _Plan
+    monkeypatch.setenv("CYBAYES_S2_TILED", "1")
+    monkeypatch.setenv("CYBAYES_S2T_SLOTS", str(slots))
+    _check_random_inputs(2, n_taxa, n_sites, model, n_cats=n_cats)
+    # same inputs through both kernels: every stored partial equal bit for bit, lnL to summation order
+    tree, root, edges, codes, amb, pi, er, rates = _random_problem(1002, n_taxa, n_sites, 2, n_cats=n_cats)
+    C = len(rates)
+    tm = [oracle.prob_t(model, model == "F81", pi, tree, er, r) for r in rates]
+    plan = _Plan(edges)
+    ekeys = list(tree.keys())
+    res = []
+    for tiled in ("1", "0"):
+        monkeypatch.setenv("CYBAYES_S2_TILED", tiled)
+        eng = Engine(codes, 2, C, amb)
+        block = eng.alloc_slots(len(ekeys) * C)
+        slot_of = {(k, e): block.base + k * len(ekeys) + i for k in range(C) for i, e in enumerate(ekeys)}
+        eng.upload_pmats(np.arange(block.base, block.base + block.n, dtype=np.int32),
+                         np.stack([tm[k][e] for k in range(C) for e in ekeys]))
+        pslots = np.array([[slot_of[k, e] for k in range(C)] for e in plan.edge_keys], dtype=np.int32)
+        lnl, snap = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=True, force_walk=True)
+        parts = {n: eng.read_partial(snap, n, with_scale=True) for n in plan.nodes.tolist()[:-1]}
+        info = eng.last_eval_info()
+        res.append((lnl, parts, info))
+        eng.close()
+    (l1, p1, i1), (l0, p0, i0) = res
+    assert abs(l1 - l0) <= 1e-13 * abs(l0)
+    for n in p1:
+        assert np.array_equal(p1[n][0], p0[n][0]) and np.array_equal(p1[n][1], p0[n][1]), n
+    assert i1["stored"] == i0["stored"] and i1["bytes_written"] == i0["bytes_written"]
+    if slots > 0 and n_taxa > 8:
+        assert i1["stack_pops"] > 0 and i1["read_back"] <= i0["read_back"]
+
+
+@pytest.mark.parametrize("name", ["narrow_F81", "ielex_multistate_F81", "phon_ringe_GTR"])
+def test_batched_spr_scoring(name, golden_cases, gpu_backend):
+    """External-SPR candidates (mcmc_gamma.pyx:136-185; the reference scores each with a full pass,
+    mat_mcmc_gamma.py:167-169) scored as ONE batch against one cache: every candidate is the two dirty paths that
+    merge at the regraft point.  Bit-identical to cache_matML per candidate; equal to the oracle's full likelihood of
+    the rearranged tree."""
+    from cybayes_b200.driver import _spr_dirty_nodes, spr_tables
+    from cybayes_b200.mcmc_gamma import adjlist2reverse_nodes_dict, externalSPR, get_prob_t
+    from cybayes_b200.ML_gamma import cache_matML, matML, score_proposals
+    case = golden_cases[name]
+    config = _setup_case(case)
+    tree, pi, rates, edges, site_rates = golden_io.case_state(case)
+    if rates is None:
+        rates = np.ones(1)
+    tmats = [get_prob_t(pi, tree, rates, r) for r in site_rates]
+    args = (config.N_SITES, config.N_TAXA, config.N_CATS)
+    root, N = case["root"], case["n_taxa"]
+    lnl, cache = matML(pi, root, config.LEAF_LLMAT, edges, tmats, *args)
+    parent_of = adjlist2reverse_nodes_dict(tree)
+    random.seed(4242)
+    proposals, trees = [], []
+    while len(proposals) < 24:
+        t2, order, hr = externalSPR(dict(tree), root)
+        if hr == 0.0:
+            continue                       # the move was a no-op
+        dirty = sorted(_spr_dirty_nodes(parent_of, t2, root))
+        proposals.append((dirty, order, spr_tables(tmats, t2, pi, rates, site_rates)))
+        trees.append(t2)
+    batch = score_proposals(pi, root, config.LEAF_LLMAT, cache, proposals)
+    single = [cache_matML(pi, root, config.LEAF_LLMAT, cache, d, o, tm, *args)[0] for d, o, tm in proposals]
+    assert batch.tolist() == [float(x) for x in single]
+    assert len(set(batch.tolist())) > 12
+    _, _, _, _, ll, _, n_sites = oracle.read_phylip(golden_io.data_path(case), case["reader"])
+    rel = REL_GTR if case["model"] == "GTR" else REL_CLOSED
+    for idx in range(0, len(proposals), 4):
+        tm_o = [oracle.prob_t(case["model"], case["dtype"] == "bin", pi, trees[idx], rates, r, beta=case["norm_beta"])
+                for r in site_rates]
+        want = oracle.mat_ml(pi, root, ll, proposals[idx][1], tm_o, n_sites, N)[0]
+        assert abs(batch[idx] - want) <= rel * abs(want), (idx, batch[idx], want)
