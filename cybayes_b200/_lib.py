@@ -43,6 +43,7 @@ SIGNATURES = {
     "cb_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "cb_mark_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cb_sync": (C.c_int, [C.c_void_p]),
+    "cb_fp64_peak": (C.c_int, [C.c_void_p, c_f64p]),
     "cb_flush_l2": (C.c_int, [C.c_void_p]),
 }
 

@@ -33,7 +33,8 @@ struct OpDesc {
   int32_t out_buf;                         // shared-memory tile buffer receiving the result, or -1
   int32_t in_buf[2];                       // kind == SRC_STACK: tile buffer holding the child
   int32_t spill;                           // stored AND read back inside the same launch: plain stores
-  int32_t pad2_[2];
+  int32_t pushed;                          // out_buf is a stack slot (the result is popped by a later op)
+  int32_t pad2_[1];
 };
 static_assert(sizeof(OpDesc) == 256, "OpDesc must stay 256 bytes");
 
@@ -62,6 +63,9 @@ struct LaunchConst {
   double cats;            // n_cats as a double (the reference divides, ML_gamma.pyx:38)
   int32_t rc_stagger;     // register-carried DMMA kernel: anti-lockstep barriers between the warps of a sub-partition
   int32_t n_amb;          // rows of `amb`
+  const void* codes;      // tip state codes [n_taxa][n_sites]
+  int32_t s2t_bulk;       // tiled 2-state kernel: stored partials leave through shared memory + bulk-async copies
+  int32_t pad_;
 };
 
 }  // namespace cb

@@ -131,7 +131,7 @@ struct PlanOp {
   int32_t node;
   PlanChild ch[2];
   int32_t out_buf;               // tiled kernel: shared-memory tile buffer of the result, or -1
-  uint8_t is_root, keep, stream, spill;
+  uint8_t is_root, keep, stream, spill, pushed;
 };
 struct PlanLaunch { int r_begin, r_end, max_ops, n_bufs; };
 struct EvalPlan {
@@ -164,7 +164,9 @@ struct cb_ctx {
   double* d_staged = nullptr;  // P matrices of the current evaluation in stage layout and consumption order
   size_t staged_bytes = 0;
   bool s2_tiled = false;  // 2-state family on a large alignment: tile-interleaved partials + prune_s2t_kernel
-  int s2t_slots = 3;      // its shared-memory stack slots per warp (tile buffers 2 .. 2 + slots - 1)
+  int s2t_slots = 4;      // its shared-memory stack slots per warp
+  int s2t_minb = 2;       // resident blocks per SM it is launched for (2: 128 registers, 4-stage image ring; 3: 85, 3-stage)
+  bool s2t_bulk = false;  // stored partials leave through staging tiles + bulk-async copies instead of plain stores
   S2TImage* d_images = nullptr;  // op images of the current evaluation (s2t_image_kernel)
   int s2_vec = 1;  // sites per thread of the 2-state kernel on large alignments
   int s2_minb = 3; // its __launch_bounds__ min blocks per SM (experiment knob)
@@ -273,10 +275,14 @@ static int create_impl(int device, cb_ctx** out) {
   if (const char* v = getenv("CYBAYES_S2_V")) c->s2_vec = (atoi(v) == 2) ? 2 : 1;
   if (const char* v = getenv("CYBAYES_S2_MINB")) c->s2_minb = (atoi(v) == 4) ? 4 : 3;
   if (getenv("CYBAYES_S2_NO_CS")) c->s2_stream_stores = false;
+  if (const char* v = getenv("CYBAYES_S2T_MINB")) c->s2t_minb = atoi(v) == 3 ? 3 : 2;
+  if (getenv("CYBAYES_S2T_BULK")) c->s2t_bulk = atoi(getenv("CYBAYES_S2T_BULK")) != 0;
+  c->s2t_slots = c->s2t_minb == 3 ? 3 : 4;
   if (const char* v = getenv("CYBAYES_S2T_SLOTS")) c->s2t_slots = std::max(0, std::min(8, atoi(v)));
   if (getenv("CYBAYES_NO_PLAN_CACHE")) c->no_plan_cache = true;
-  CU(cudaFuncSetAttribute(prune_s2t_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));  // + 384 B static
-  CU(cudaFuncSetAttribute(prune_s2t_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+#define CB_S2T_ATTR(CC, MB) CU(cudaFuncSetAttribute(prune_s2t_kernel<CC, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024))
+  CB_S2T_ATTR(4, 2); CB_S2T_ATTR(4, 3); CB_S2T_ATTR(1, 2); CB_S2T_ATTR(1, 3);   // + 384 B static each
+#undef CB_S2T_ATTR
   CU(cudaFuncSetAttribute(prune_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #define CB_DMMA_ATTR(SS) CU(cudaFuncSetAttribute(prune_dmma_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
   CB_DMMA_ATTR(0); CB_DMMA_ATTR(32); CB_DMMA_ATTR(40); CB_DMMA_ATTR(47); CB_DMMA_ATTR(48); CB_DMMA_ATTR(56); CB_DMMA_ATTR(64);
@@ -794,6 +800,9 @@ static LaunchConst make_const(cb_ctx* c) {
   k.cats = (double)c->n_cats;
   k.rc_stagger = c->rc_stagger;
   k.n_amb = c->n_amb;
+  k.codes = c->d_codes;
+  k.s2t_bulk = c->s2t_bulk ? 1 : 0;
+  k.pad_ = 0;
   return k;
 }
 
@@ -820,12 +829,14 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
   kk.ranges = k.ranges + r_begin;
   if (c->s2_tiled) {
     // large binary alignments: tile-interleaved partials, shared-memory stack, bulk-async stores (kernels_s2t.cuh)
-    const size_t smem = s2t_smem_bytes(n_bufs, c->n_cats);
+    const size_t smem = s2t_smem_bytes(n_bufs, c->n_cats, c->s2t_minb);
     REQUIRE(smem <= (size_t)226 * 1024, "internal error: %d tile buffers do not fit shared memory", n_bufs);
     const int64_t n_tiles = c->P / S2T_W;
     dim3 grid((unsigned)((n_tiles + S2T_WARPS - 1) / S2T_WARPS), (unsigned)n_r);
-    if (c->n_cats == 4) prune_s2t_kernel<4><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
-    else prune_s2t_kernel<1><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
+    if (c->n_cats == 4 && c->s2t_minb == 3) prune_s2t_kernel<4, 3><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
+    else if (c->n_cats == 4) prune_s2t_kernel<4, 2><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
+    else if (c->s2t_minb == 3) prune_s2t_kernel<1, 3><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
+    else prune_s2t_kernel<1, 2><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
   } else if (c->family_s2) {
     // Fixed per alignment (independent of the schedule) so the reduction order never changes:
     // 64-thread blocks, one site per thread, to spread a small alignment over the SMs (the tiled kernel above
@@ -900,6 +911,7 @@ static int materialize_cherry(cb_ctx* c, int rec, int* buf_out) {
   op.dst = c->buffers[bi].data;
   op.dst_scale = c->buffers[bi].scale;
   op.out_buf = -1;
+  op.pushed = 0;
   for (int kx = 0; kx < 2; ++kx) {
     op.kind[kx] = SRC_TIP;
     op.src[kx] = (const char*)c->d_codes + (size_t)(c->recs[rec].tip[kx] - 1) * c->P * c->code_bytes;
@@ -943,6 +955,7 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
   const bool want_snap = (flags & CB_EVAL_WANT_SNAPSHOT) != 0;
   const bool store_root = (flags & CB_EVAL_STORE_ROOT) != 0;
   const int K = c->s2_tiled ? c->s2t_slots : 0;  // stack slots of the kernel
+  const int slot_base = c->s2t_bulk ? S2T_STAGING : 0;  // tile buffers below it are the staging buffers of the bulk-store path
   plan.ops.clear(); plan.ranges.clear(); plan.launches.clear();
   plan.bytes_written = plan.bytes_read = 0;
   plan.n_stored = plan.n_buffer_reads = plan.n_stack = plan.n_spills = plan.n_cherries = 0;
@@ -1123,7 +1136,7 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
               const int x = fk == 0 ? a : b2, y = fk == 0 ? b2 : a;
               if (t.phase == 0) { t.phase = 1; fr.push_back({x, kk, 0}); continue; }
               if (t.phase == 1) {
-                push_slot[x] = kk > 0 ? S2T_STAGING + (K - kk) : -1;
+                push_slot[x] = kk > 0 ? slot_base + (K - kk) : -1;
                 t.phase = 2;
                 fr.push_back({y, kk > 0 ? kk - 1 : 0, 0});
                 continue;
@@ -1168,7 +1181,7 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
       po.node = L[j].node;
       po.is_root = (j == n - 1);
       REQUIRE(!po.is_root || p == n - 1, "internal error: root is not last");
-      po.keep = po.stream = po.spill = 0;
+      po.keep = po.stream = po.spill = po.pushed = 0;
       po.out_buf = -1;
       for (int kx = 0; kx < 2; ++kx) {
         PlanChild& pc = po.ch[kx];
@@ -1209,6 +1222,13 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
       }
     }
     plan.bytes_read += c->P * 8;  // pattern weights at the root
+    if (c->s2_tiled)  // the tiled kernel wants the children in canonical order (products and exponent sums commute exactly)
+      for (int p = 0; p < n; ++p) {
+        PlanOp& po = plan.ops[base + p];
+        if (s2t_rank(po.ch[1].kind) < s2t_rank(po.ch[0].kind)) std::swap(po.ch[0], po.ch[1]);
+        REQUIRE(s2t_combo(po.ch[0].kind, po.ch[1].kind) >= 0, "internal error: op of node %d has children of kinds %d, %d", po.node,
+                po.ch[0].kind, po.ch[1].kind);
+      }
     for (int p = 0; p < n; ++p) {
       const int j = order[p];
       PlanOp& po = plan.ops[base + p];
@@ -1221,8 +1241,8 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
         if (po.spill) plan.n_spills++;
       }
       if (c->s2_tiled) {
-        if (push_slot[j] >= 0 && !po.is_root) po.out_buf = push_slot[j];
-        else if (po.keep && !po.spill) { po.out_buf = staging_rr; staging_rr ^= 1; }
+        if (push_slot[j] >= 0 && !po.is_root) { po.out_buf = push_slot[j]; po.pushed = 1; }
+        else if (c->s2t_bulk && po.keep && !po.spill) { po.out_buf = staging_rr; staging_rr ^= 1; }
       }
     }
 
@@ -1382,6 +1402,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     op.is_root = po.is_root;
     op.pad_ = po.stream;
     op.spill = po.spill;
+    op.pushed = po.pushed;
     op.out_buf = po.out_buf;
     op.dst = nullptr;
     op.dst_scale = nullptr;
@@ -1633,6 +1654,46 @@ extern "C" int cb_sync(cb_ctx* c) {
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
+// FP64 tensor peak of this GPU, measured from registers: every warp keeps 4 independent DMMA m8n8k4 accumulator
+// chains going (16 warps per SM).  The denominator of the S = 64 roofline in bench.py (MEASURED_PEAKS.json has no
+// FP64 figure).
+__global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters) {
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0, c5 = 0.0, c6 = 0.0, c7 = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      rc_dmma(c0, c1, a, b);
+      rc_dmma(c2, c3, a, b);
+      rc_dmma(c4, c5, a, b);
+      rc_dmma(c6, c7, a, b);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
+}
+extern "C" int cb_fp64_peak(cb_ctx* c, double* tflops_out) {
+  REQUIRE(c && tflops_out, "null argument");
+  CU(cudaSetDevice(c->device));
+  const int blocks = c->sm_count, threads = 512, iters = 20000;
+  double* d = nullptr;
+  CU(cudaMalloc(&d, (size_t)blocks * threads * 8));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+    CU(cudaEventRecord(c->ev_mark[0], c->stream));
+    fp64_peak_kernel<<<blocks, threads, 0, c->stream>>>(d, iters);
+    CU(cudaEventRecord(c->ev_mark[1], c->stream));
+    CU(cudaEventSynchronize(c->ev_mark[1]));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev_mark[0], c->ev_mark[1]));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  CU(cudaGetLastError());
+  cudaFree(d);
+  const double flops = (double)blocks * (threads / 32) * (double)iters * 32.0 * 512.0;  // 32 DMMAs per iteration, 2*8*8*4 flop each
+  *tflops_out = flops / (best * 1e-3) / 1e12;
+  return 0;
+}
 extern "C" int cb_flush_l2(cb_ctx* c) {
   REQUIRE(c, "null argument");
   CU(cudaSetDevice(c->device));
@@ -1641,5 +1702,132 @@ extern "C" int cb_flush_l2(cb_ctx* c) {
     if (dev_alloc(c, &c->d_flush, c->flush_bytes)) return 1;
   }
   CU(cudaMemsetAsync(c->d_flush, 0x5a, c->flush_bytes, c->stream));
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------- native generation loop
+#include "mcmc_native.cuh"
+
+struct cb_chain {
+  cbm::Chain ch;
+};
+static int chain_err(cb_chain* c, int rc) {
+  if (rc && !c->ch.err.empty()) {
+    g_err = c->ch.err;
+    c->ch.err.clear();
+  }
+  return rc;
+}
+extern "C" int cb_chain_create(cb_ctx* ctx, const cb_chain_backend* be, int n_taxa, int n_states, int n_cats, int model, int binary,
+                               int root, int slot_base, int slot_count, int host_exp_max, int n_params, const int32_t* param_ids,
+                               const double* params_cdf, const double* tree_cdf, const double* bl_cdf, cb_chain** out) {
+  return guarded([&] {
+    REQUIRE(be && out && param_ids && params_cdf && tree_cdf && bl_cdf, "null argument");
+    REQUIRE(ctx || (be->pmat_build && be->eval && be->snapshot_release), "a chain needs a context or a full backend");
+    REQUIRE(be->site_rates && be->f81_beta && be->gtr_eig, "host callbacks are required");
+    REQUIRE(n_taxa >= 2 && n_states >= 2 && n_cats >= 1 && n_cats <= CB_MAX_CATS && model >= 0 && model <= 2, "bad chain shape");
+    REQUIRE(root == 2 * n_taxa - 1, "root must be node 2 * n_taxa - 1 (mcmc_gamma.pyx:270-287)");
+    REQUIRE(slot_count >= 2 * (2 * n_taxa - 2) * n_cats + 8 * n_cats, "slot range too small for the chain");
+    cb_chain* c = new cb_chain();
+    cbm::Chain& ch = c->ch;
+    ch.ctx = ctx;
+    ch.be = *be;
+    ch.n_taxa = n_taxa; ch.S = n_states; ch.C = n_cats; ch.model = model; ch.binary = binary != 0; ch.root = root;
+    ch.host_exp_max = host_exp_max;
+    ch.param_ids.assign(param_ids, param_ids + n_params);
+    ch.params_cdf.assign(params_cdf, params_cdf + n_params);
+    ch.tree_cdf.assign(tree_cdf, tree_cdf + 2);
+    ch.bl_cdf.assign(bl_cdf, bl_cdf + 2);
+    for (int i = slot_count - 1; i >= 0; --i) ch.free_slots.push_back(slot_base + i);
+    for (auto& w : ch.py.mt) w = 0;
+    for (auto& w : ch.np_.mt) w = 0;
+    *out = c;
+    return 0;
+  });
+}
+extern "C" int cb_chain_set_state(cb_chain* c, int n_edges, const int32_t* parents, const int32_t* children, const double* lengths,
+                                  const double* pi, int n_rates, const double* rates, double alpha, const double* site_rates, double beta,
+                                  const double* gtr_eig, double* lnl_out) {
+  return guarded([&] {
+    REQUIRE(c && parents && children && lengths && pi && rates && site_rates, "null argument");
+    cbm::Chain& ch = c->ch;
+    REQUIRE(n_edges == 2 * ch.n_taxa - 2, "a rooted binary tree on %d taxa has %d edges", ch.n_taxa, 2 * ch.n_taxa - 2);
+    REQUIRE(ch.model != 2 || gtr_eig, "GTR needs the eigensystem of the start state");
+    for (const cbm::Edge& e : ch.tree) cbm::free_slots(&ch, e.slot, ch.C);
+    cbm::be_release(&ch, ch.snap);
+    ch.snap = -1;
+    ch.tree.clear();
+    for (int i = 0; i < n_edges; ++i) {
+      REQUIRE(parents[i] > ch.n_taxa && parents[i] < 2 * ch.n_taxa && children[i] >= 1 && children[i] < 2 * ch.n_taxa, "bad edge %d", i);
+      ch.tree.push_back(cbm::Edge{parents[i], children[i], lengths[i], {0}});
+    }
+    ch.pi.assign(pi, pi + ch.S);
+    ch.rates.assign(rates, rates + n_rates);
+    ch.site_rates.assign(site_rates, site_rates + ch.C);
+    ch.alpha = alpha;
+    ch.beta = beta;
+    ch.gtr.clear();
+    if (gtr_eig) ch.gtr.assign(gtr_eig, gtr_eig + ch.S + 2 * (size_t)ch.S * ch.S);
+    if (chain_err(c, cbm::build_all(&ch, ch.tree, ch.pi.data(), ch.beta, ch.gtr.data(), ch.site_rates.data()))) return 1;
+    std::vector<int32_t> k0, k1, par;
+    cbm::build_kids(&ch, ch.tree, k0, k1, par);
+    for (int nd = ch.n_taxa + 1; nd < 2 * ch.n_taxa; ++nd) REQUIRE(k0[nd] >= 0 && k1[nd] >= 0, "node %d does not have two children", nd);
+    cbm::plan_nodes(&ch, k0, k1);
+    REQUIRE((int)ch.order_nodes.size() == ch.n_taxa - 1, "the edges do not form a tree rooted at %d", ch.root);
+    if (chain_err(c, cbm::evaluate(&ch, ch.tree, k0, k1, ch.order_nodes, -1, ch.pi.data(), &ch.snap, &ch.lnl))) return 1;
+    if (lnl_out) *lnl_out = ch.lnl;
+    return 0;
+  });
+}
+extern "C" int cb_chain_set_rng(cb_chain* c, const uint32_t* py_mt, int py_pos, const uint32_t* np_mt, int np_pos) {
+  REQUIRE(c && py_mt && np_mt && py_pos >= 0 && py_pos <= 624 && np_pos >= 0 && np_pos <= 624, "bad generator state");
+  memcpy(c->ch.py.mt, py_mt, sizeof c->ch.py.mt);
+  memcpy(c->ch.np_.mt, np_mt, sizeof c->ch.np_.mt);
+  c->ch.py.pos = py_pos;
+  c->ch.np_.pos = np_pos;
+  return 0;
+}
+extern "C" int cb_chain_get_rng(cb_chain* c, uint32_t* py_mt, int* py_pos, uint32_t* np_mt, int* np_pos) {
+  REQUIRE(c && py_mt && np_mt && py_pos && np_pos, "null argument");
+  memcpy(py_mt, c->ch.py.mt, sizeof c->ch.py.mt);
+  memcpy(np_mt, c->ch.np_.mt, sizeof c->ch.np_.mt);
+  *py_pos = c->ch.py.pos;
+  *np_pos = c->ch.np_.pos;
+  return 0;
+}
+extern "C" int cb_chain_run(cb_chain* c, int64_t n_gens, int8_t* move, int8_t* accepted, double* current_ll, double* proposed_ll,
+                            double* ll_ratio, double* log_u) {
+  return guarded([&] {
+    REQUIRE(c && n_gens >= 0 && c->ch.snap >= 0, "cb_chain_set_state must come first");
+    return chain_err(c, cbm::run(&c->ch, n_gens, move, accepted, current_ll, proposed_ll, ll_ratio, log_u));
+  });
+}
+extern "C" int cb_chain_get_state(cb_chain* c, int32_t* parents, int32_t* children, double* lengths, double* pi, double* rates,
+                                  double* alpha, double* site_rates, double* lnl) {
+  REQUIRE(c, "null argument");
+  const cbm::Chain& ch = c->ch;
+  for (size_t i = 0; i < ch.tree.size(); ++i) {
+    if (parents) parents[i] = ch.tree[i].p;
+    if (children) children[i] = ch.tree[i].c;
+    if (lengths) lengths[i] = ch.tree[i].t;
+  }
+  if (pi) memcpy(pi, ch.pi.data(), ch.pi.size() * 8);
+  if (rates) memcpy(rates, ch.rates.data(), ch.rates.size() * 8);
+  if (alpha) *alpha = ch.alpha;
+  if (site_rates) memcpy(site_rates, ch.site_rates.data(), ch.site_rates.size() * 8);
+  if (lnl) *lnl = ch.lnl;
+  return 0;
+}
+extern "C" int cb_chain_counters(cb_chain* c, int64_t* moves7, int64_t* accepts7) {
+  REQUIRE(c && moves7 && accepts7, "null argument");
+  memcpy(moves7, c->ch.n_moves, sizeof c->ch.n_moves);
+  memcpy(accepts7, c->ch.n_accepts, sizeof c->ch.n_accepts);
+  return 0;
+}
+extern "C" int cb_chain_destroy(cb_chain* c) {
+  if (!c) return 0;
+  cbm::be_release(&c->ch, c->ch.snap);
+  delete c;
   return 0;
 }

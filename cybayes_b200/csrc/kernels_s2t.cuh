@@ -16,7 +16,9 @@
 //     read back from L2/HBM.  The host orders the walk (dynamic programme over the tree, cybayes_b200.cu) so
 //     that almost every such child fits the K slots (C4: 1 of 210 misses with K = 4, 31 with K = 3); the
 //     misses ("spills") go through global memory with plain stores/loads.  In steady state the kernel issues
-//     NO global loads except the tip codes (1 byte per site and tip, prefetched one op ahead).
+//     NO register-destination global loads: the tip codes (1 byte per site and tip) arrive in shared memory through
+//     4-byte cp.async copies issued two ops ahead (a load into a register would tie the op to a scoreboard that
+//     unrelated instructions end up waiting on -- measured: 13 % of all stall samples on one integer add).
 //   * Op images.  Everything a block used to recompute per op while staging (P rows with the missing-data
 //     column, the 9-row lookup tables of folded cherries) is built ONCE per evaluation by s2t_image_kernel
 //     into a 1408-byte image per op; the main kernel streams the images of its range through a two-chunk ring
@@ -31,8 +33,10 @@ namespace cb {
 constexpr int S2T_W = 32;          // sites per tile (one warp)
 constexpr int S2T_WARPS = 8;       // warps per block
 constexpr int S2T_THREADS = S2T_W * S2T_WARPS;
-constexpr int S2T_RING_OPS = 8;    // op images per ring chunk (two chunks in flight)
-constexpr int S2T_STAGING = 2;     // tile buffers 0..1 per warp rotate as store staging; stack slots follow
+constexpr int S2T_RING_OPS = 4;    // op images per ring chunk
+__host__ __device__ constexpr int s2t_ring_stages(int minb) { return minb >= 3 ? 3 : 4; }  // chunks in the ring: a refill has
+                                                                                         // (stages - 1) chunks of slack
+constexpr int S2T_STAGING = 2;     // bulk-store path only: tile buffers 0..1 per warp rotate as store staging, stack slots follow
 
 __host__ __device__ constexpr int s2t_tile_bytes(int C) { return S2T_W * (2 * C * 8 + 4); }
 
@@ -41,18 +45,49 @@ struct S2TImage {
   double tab[2][s2_child_stage(CB_S2_MAX_CATS)];  // per child: see s2_child_stage (P rows / tip rows / cherry table)
   char* dst;                 // tile-layout partial buffer, or nullptr (not stored)
   const char* src[2];        // SRC_BUFFER: tile-layout partial buffer; SRC_TIP: code row
-  const void* ctip[2][2];    // SRC_CHERRY: code rows of the cherry's two tips
-  int32_t kind[2];
+  const void* rows[4];       // code rows the op reads, at fixed positions: child 0 -> [0] (tip / cherry tip a), [1] (cherry
+                             // tip b); child 1 -> [2], [3]; unused positions point at a valid row (loaded, ignored)
+  int32_t kind[2];           // canonical order (s2t_rank): the host swaps the children when needed
   int32_t is_root;
-  int32_t spill;             // 1: the stored partial is read back by a later op of this launch -> plain stores
+  int32_t combo;             // S2TCombo: the pair of child kinds, selects the specialised op body
   int32_t out_buf;           // shared-memory tile buffer that receives the result (-1: registers only)
   int32_t in_buf[2];         // SRC_STACK: tile buffer holding the child
-  int32_t pad_[3];
+  int32_t store_mode;        // S2TStore
+  int32_t pad_[2];
 };
 static_assert(sizeof(S2TImage) == 1408, "S2TImage must stay 1408 bytes (a multiple of 16)");
 
-__host__ __device__ inline size_t s2t_smem_bytes(int n_bufs, int C) {
-  return (size_t)2 * S2T_RING_OPS * sizeof(S2TImage) + (size_t)S2T_WARPS * n_bufs * s2t_tile_bytes(C) + 64;
+// Children of an op are kept in a canonical order (products and exponent sums commute exactly), which leaves ten
+// possible pairs of child kinds; each has its own straight-line op body in the kernel.
+__host__ __device__ constexpr int s2t_rank(int kind) {
+  return kind == SRC_CARRIED ? 0 : kind == SRC_STACK ? 1 : kind == SRC_BUFFER ? 2 : kind == SRC_TIP ? 3 : 4;
+}
+enum S2TCombo : int32_t {
+  S2T_CARRIED_STACK = 0, S2T_CARRIED_BUFFER, S2T_CARRIED_TIP, S2T_CARRIED_CHERRY, S2T_BUFFER_BUFFER, S2T_BUFFER_TIP,
+  S2T_BUFFER_CHERRY, S2T_TIP_TIP, S2T_TIP_CHERRY, S2T_CHERRY_CHERRY, S2T_N_COMBOS
+};
+__host__ __device__ inline int s2t_combo(int k0, int k1) {   // kinds in canonical order; -1: not a pair the walk produces
+  if (k0 == SRC_CARRIED) return k1 == SRC_STACK ? S2T_CARRIED_STACK : k1 == SRC_BUFFER ? S2T_CARRIED_BUFFER : k1 == SRC_TIP ? S2T_CARRIED_TIP : k1 == SRC_CHERRY ? S2T_CARRIED_CHERRY : -1;
+  if (k0 == SRC_BUFFER) return k1 == SRC_BUFFER ? S2T_BUFFER_BUFFER : k1 == SRC_TIP ? S2T_BUFFER_TIP : k1 == SRC_CHERRY ? S2T_BUFFER_CHERRY : -1;
+  if (k0 == SRC_TIP) return k1 == SRC_TIP ? S2T_TIP_TIP : k1 == SRC_CHERRY ? S2T_TIP_CHERRY : -1;
+  if (k0 == SRC_CHERRY) return k1 == SRC_CHERRY ? S2T_CHERRY_CHERRY : -1;
+  return -1;
+}
+// how the result of an op leaves the registers
+enum S2TStore : int32_t {
+  S2T_ST_NONE = 0,     // carried only
+  S2T_ST_SMEM = 1,     // into a stack slot in shared memory (out_buf)
+  S2T_ST_GLOBAL = 2,   // plain coalesced stores to the buffer tile (the tile is contiguous: nine 256-byte rows back to back)
+  S2T_ST_STREAM = 4,   // ... with the streaming (evict-first) hint: nobody reads the partial back in this evaluation
+  S2T_ST_BULK = 8      // through a tile buffer in shared memory (out_buf) and one bulk-async copy (CYBAYES_S2T_BULK=1)
+};
+
+constexpr int S2T_CODE_SLOTS = 4;  // per warp: tip codes of 4 consecutive ops (4 rows x 32 sites x 1 byte each), cp.async ring
+constexpr int S2T_CODE_BYTES = S2T_CODE_SLOTS * 4 * S2T_W;
+
+__host__ __device__ inline size_t s2t_smem_bytes(int n_bufs, int C, int minb) {
+  return (size_t)s2t_ring_stages(minb) * S2T_RING_OPS * sizeof(S2TImage) + (size_t)S2T_WARPS * S2T_CODE_BYTES +
+         (size_t)S2T_WARPS * n_bufs * s2t_tile_bytes(C) + 64;
 }
 
 // ---------------------------------------------------------------------------------------- PTX helpers
@@ -93,6 +128,15 @@ __device__ __forceinline__ void s2t_bulk_wait_read() {
 }
 __device__ __forceinline__ void s2t_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void s2t_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// 4-byte asynchronous copy global -> shared (LDGSTS): no destination register, completion tracked per thread in groups
+__device__ __forceinline__ void s2t_cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s2t_smem_addr(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void s2t_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void s2t_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------ pre-pass
 // One block (32 threads) per op: descriptor + per-child tables.  Exactly the arithmetic prune_s2_kernel does
@@ -109,14 +153,25 @@ __global__ void __launch_bounds__(32) s2t_image_kernel(const LaunchConst k, int 
     im->dst = reinterpret_cast<char*>(op->dst);
     im->src[0] = static_cast<const char*>(op->src[0]);
     im->src[1] = static_cast<const char*>(op->src[1]);
-    im->ctip[0][0] = op->ctip[0][0]; im->ctip[0][1] = op->ctip[0][1];
-    im->ctip[1][0] = op->ctip[1][0]; im->ctip[1][1] = op->ctip[1][1];
+    for (int ch = 0; ch < 2; ++ch) {
+      const int kind = op->kind[ch];
+      im->rows[2 * ch] = kind == SRC_TIP ? op->src[ch] : kind == SRC_CHERRY ? op->ctip[ch][0] : k.codes;
+      im->rows[2 * ch + 1] = kind == SRC_CHERRY ? op->ctip[ch][1] : k.codes;
+    }
     im->kind[0] = op->kind[0]; im->kind[1] = op->kind[1];
     im->is_root = op->is_root;
-    im->spill = op->spill;
+    im->combo = s2t_combo(op->kind[0], op->kind[1]);
     im->out_buf = op->out_buf;
     im->in_buf[0] = op->in_buf[0]; im->in_buf[1] = op->in_buf[1];
-    im->pad_[0] = im->pad_[1] = im->pad_[2] = 0;
+    // out_buf names a stack slot (the op is pushed) or a staging buffer of the bulk-store path
+    const bool stored = op->dst != nullptr, pushed = op->pushed != 0, staged = op->out_buf >= 0 && !pushed;
+    int mode = pushed ? S2T_ST_SMEM : S2T_ST_NONE;
+    if (stored) {
+      if (staged || (pushed && k.s2t_bulk && !op->spill)) mode |= S2T_ST_BULK;
+      else mode |= S2T_ST_GLOBAL | (op->pad_ ? S2T_ST_STREAM : 0);
+    }
+    im->store_mode = mode;
+    im->pad_[0] = im->pad_[1] = 0;
   }
   // P matrices of internal and tip children (one thread per child, category and row)
   for (int idx = t; idx < 4 * C; idx += 32) {
@@ -184,34 +239,95 @@ __global__ void __launch_bounds__(32) s2t_image_kernel(const LaunchConst k, int 
 }
 
 // ---------------------------------------------------------------------------------------- main kernel
-__device__ __forceinline__ void s2t_fetch_codes(const S2TImage& im, int code_bytes, int64_t site, unsigned (&code)[2][2]) {
+// contribution of one child to the op's product: FIRST initialises acc, the second child multiplies into it.
+// codes: this op's slot of the warp's code ring, [row q][site]: child 0 uses rows 0, 1, child 1 rows 2, 3.
+template <int C, int KIND, int CH, bool FIRST>
+__device__ __forceinline__ void s2t_child(const S2TImage& im, const double (&cur)[C][2], int cur_e, const unsigned char* codes,
+                                          const unsigned char* mybufs, size_t tile_off, int lane, double (&acc)[C][2], int& e_in) {
+  constexpr int TB = s2t_tile_bytes(C);
+  const double* pbase = &im.tab[CH][0];
+  if constexpr (KIND == SRC_CARRIED || KIND == SRC_STACK || KIND == SRC_BUFFER) {
+    double L[C][2];
+    int se;
+    if constexpr (KIND == SRC_CARRIED) {
 #pragma unroll
-  for (int ch = 0; ch < 2; ++ch) {
-    if (im.kind[ch] == SRC_TIP) {
-      unsigned c1[1];
-      load_codes<1>(im.src[ch], code_bytes, site, c1);
-      code[ch][0] = c1[0];
-    } else if (im.kind[ch] == SRC_CHERRY) {
-      unsigned c1[1];
-      load_codes<1>(im.ctip[ch][0], code_bytes, site, c1);
-      code[ch][0] = c1[0];
-      load_codes<1>(im.ctip[ch][1], code_bytes, site, c1);
-      code[ch][1] = c1[0];
+      for (int c = 0; c < C; ++c) { L[c][0] = cur[c][0]; L[c][1] = cur[c][1]; }
+      se = cur_e;
+    } else if constexpr (KIND == SRC_STACK) {
+      const double* sb = reinterpret_cast<const double*>(mybufs + (size_t)im.in_buf[CH] * TB);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        L[c][0] = sb[(2 * c) * S2T_W + lane];
+        L[c][1] = sb[(2 * c + 1) * S2T_W + lane];
+      }
+      se = reinterpret_cast<const int*>(sb + 2 * C * S2T_W)[lane];
+    } else {
+      const double* gb = reinterpret_cast<const double*>(im.src[CH] + tile_off);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        L[c][0] = __ldcg(gb + (2 * c) * S2T_W + lane);
+        L[c][1] = __ldcg(gb + (2 * c + 1) * S2T_W + lane);
+      }
+      se = __ldcg(reinterpret_cast<const int*>(gb + 2 * C * S2T_W) + lane);
     }
+    const double2* pm = reinterpret_cast<const double2*>(pbase);   // (P[i][0], P[i][1]) broadcasts
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double2 pr = pm[c * 2 + i];
+        const double x = fma(pr.y, L[c][1], pr.x * L[c][0]);      // v[i] = P[i][0] L[0] + P[i][1] L[1]
+        if (FIRST) acc[c][i] = x; else acc[c][i] *= x;
+      }
+    }
+    if (FIRST) e_in = se; else e_in += se;
+  } else if constexpr (KIND == SRC_TIP) {
+    // state code 0 / 1 / 2 ('?', '-', '0/1') selects the staged contribution of this edge
+    const double* row = pbase + min((unsigned)codes[(2 * CH) * S2T_W + lane], 2u);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double x = row[(c * 2 + i) * 4];
+        if (FIRST) acc[c][i] = x; else acc[c][i] *= x;
+      }
+    }
+    if (FIRST) e_in = 0;
+  } else {  // folded cherry: the pair of tip codes selects a precomputed row
+    const unsigned ca = min((unsigned)codes[(2 * CH) * S2T_W + lane], 2u), cb_ = min((unsigned)codes[(2 * CH + 1) * S2T_W + lane], 2u);
+    const double* tab = pbase + (ca * 3 + cb_) * (2 * C + 1);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double x = tab[c * 2 + i];
+        if (FIRST) acc[c][i] = x; else acc[c][i] *= x;
+      }
+    }
+    if (FIRST) e_in = (int)tab[2 * C]; else e_in += (int)tab[2 * C];
   }
 }
 
-template <int C>
-__global__ void __launch_bounds__(S2T_THREADS, 2) prune_s2t_kernel(const LaunchConst k, const S2TImage* __restrict__ images,
-                                                                    int n_bufs) {
+template <int C, int K0, int K1>
+__device__ __forceinline__ void s2t_pair(const S2TImage& im, const double (&cur)[C][2], int cur_e, const unsigned char* codes,
+                                         const unsigned char* mybufs, size_t tile_off, int lane, double (&out)[C][2], int& e_in) {
+  s2t_child<C, K0, 0, true>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in);
+  s2t_child<C, K1, 1, false>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in);
+}
+
+// MINB: resident blocks per SM the kernel is compiled for (2: up to 128 registers, 3: up to 85)
+template <int C, int MINB>
+__global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const LaunchConst k, const S2TImage* __restrict__ images,
+                                                                       int n_bufs) {
   static_assert(C <= CB_S2_MAX_CATS, "2-state kernel supports at most CB_S2_MAX_CATS categories");
   constexpr int TB = s2t_tile_bytes(C);
-  constexpr int CHUNK_BYTES = S2T_RING_OPS * (int)sizeof(S2TImage);
+  constexpr int S2T_RING_STAGES = s2t_ring_stages(MINB);
+  constexpr int RING = S2T_RING_OPS * S2T_RING_STAGES;
   extern __shared__ __align__(128) unsigned char s2t_smem[];
   __shared__ double red[32];
   __shared__ int last_flag;
-  __shared__ int done_cnt[2];
-  __shared__ __align__(8) unsigned long long full_bar[2];
+  __shared__ int done_cnt[S2T_RING_STAGES];
+  __shared__ __align__(8) unsigned long long full_bar[S2T_RING_STAGES];
 
   const RangeDesc rg = k.ranges[blockIdx.y];
   const int nops = rg.end - rg.begin;
@@ -219,7 +335,8 @@ __global__ void __launch_bounds__(S2T_THREADS, 2) prune_s2t_kernel(const LaunchC
   const S2TImage* __restrict__ gimg = images + rg.begin;
   S2TImage* ring = reinterpret_cast<S2TImage*>(s2t_smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* mybufs = s2t_smem + (size_t)2 * CHUNK_BYTES + (size_t)warp * n_bufs * TB;
+  unsigned char* mycodes = s2t_smem + (size_t)RING * sizeof(S2TImage) + (size_t)warp * S2T_CODE_BYTES;
+  unsigned char* mybufs = s2t_smem + (size_t)RING * sizeof(S2TImage) + (size_t)S2T_WARPS * S2T_CODE_BYTES + (size_t)warp * n_bufs * TB;
 
   const int64_t n_tiles = k.n_sites / S2T_W;
   const int64_t tile = (int64_t)blockIdx.x * S2T_WARPS + warp;
@@ -229,21 +346,32 @@ __global__ void __launch_bounds__(S2T_THREADS, 2) prune_s2t_kernel(const LaunchC
   const int64_t site = tile * S2T_W + lane;
   const size_t tile_off = (size_t)tile * TB;
 
-  auto issue_chunk = [&](int c) {  // one thread: bulk-load the images of chunk c into its ring half
-    const int b = c & 1;
+  auto issue_chunk = [&](int c) {  // one thread: bulk-load the images of chunk c into its ring stage
+    const int b = c % S2T_RING_STAGES;
     const int n = min(S2T_RING_OPS, nops - c * S2T_RING_OPS);
     const unsigned bytes = (unsigned)n * (unsigned)sizeof(S2TImage);
     s2t_mbar_expect_tx(&full_bar[b], bytes);
     s2t_bulk_g2s(ring + (size_t)b * S2T_RING_OPS, gimg + (size_t)c * S2T_RING_OPS, bytes, &full_bar[b]);
   };
+  // the warp's tip codes of op o: lane = 8 q + j copies bytes [4 j, 4 j + 4) of the tile's 32 codes of row q
+  const int64_t code_off = tile * S2T_W + 4 * (lane & 7);
+  auto issue_codes = [&](int o) {
+    const S2TImage& im = ring[o % RING];
+    s2t_cp_async4(mycodes + (o % S2T_CODE_SLOTS) * (4 * S2T_W) + 4 * lane, static_cast<const char*>(im.rows[lane >> 3]) + code_off);
+  };
+  auto wait_chunk_of = [&](int o) {  // the image of op o is in the ring (o is the first op of its chunk)
+    const int c1 = o / S2T_RING_OPS;
+    s2t_mbar_wait(&full_bar[c1 % S2T_RING_STAGES], (unsigned)(c1 / S2T_RING_STAGES) & 1u);
+  };
 
   if (threadIdx.x == 0) {
-    s2t_mbar_init(&full_bar[0], 1);
-    s2t_mbar_init(&full_bar[1], 1);
-    done_cnt[0] = done_cnt[1] = 0;
+#pragma unroll
+    for (int b = 0; b < S2T_RING_STAGES; ++b) {
+      s2t_mbar_init(&full_bar[b], 1);
+      done_cnt[b] = 0;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    issue_chunk(0);
-    if (n_chunks > 1) issue_chunk(1);
+    for (int c = 0; c < S2T_RING_STAGES && c < n_chunks; ++c) issue_chunk(c);
   }
   __syncthreads();
 
@@ -253,110 +381,47 @@ __global__ void __launch_bounds__(S2T_THREADS, 2) prune_s2t_kernel(const LaunchC
     int cur_e = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) cur[c][0] = cur[c][1] = 0.0;
-    unsigned code_next[2][2] = {{0u, 0u}, {0u, 0u}};
     bool groups_pending = false;
 
-    s2t_mbar_wait(&full_bar[0], 0);
-    s2t_fetch_codes(ring[0], k.code_bytes, site, code_next);
+    // code pipeline: the copies of op o + 2 are issued at the end of op o; one commit group per op
+    wait_chunk_of(0);
+    issue_codes(0);
+    s2t_cp_async_commit();
+    if (nops > 1) {
+      if (S2T_RING_OPS == 1) wait_chunk_of(1);
+      issue_codes(1);
+    }
+    s2t_cp_async_commit();
 
 #pragma unroll 1
     for (int o = 0; o < nops; ++o) {
-      const int chunk = o / S2T_RING_OPS, oc = o - chunk * S2T_RING_OPS;
-      const S2TImage& im = ring[(size_t)(chunk & 1) * S2T_RING_OPS + oc];
-      unsigned code[2][2];
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-        for (int t = 0; t < 2; ++t) code[ch][t] = code_next[ch][t];
-      if (o + 1 < nops) {  // tip codes one op ahead; entering a new chunk also pulls the following chunk's tips to L2
-        const int c1 = (o + 1) / S2T_RING_OPS, o1 = (o + 1) - c1 * S2T_RING_OPS;
-        if (o1 == 0) {
-          s2t_mbar_wait(&full_bar[c1 & 1], (unsigned)(c1 >> 1) & 1u);
-          const int nxt0 = (c1 + 1) * S2T_RING_OPS;  // first op of the chunk after the one we enter
-          const int e = nxt0 + (lane >> 2);
-          if (e < nops && warp == c1 % n_active) {  // one warp per block and chunk does it
-            const OpDesc* __restrict__ dn = k.ops + rg.begin + e;
-            const int ch = (lane >> 1) & 1, t = lane & 1;
-            const int kind = dn->kind[ch];
-            const void* row = kind == SRC_TIP ? (t == 0 ? dn->src[ch] : nullptr) : (kind == SRC_CHERRY ? dn->ctip[ch][t] : nullptr);
-            if (row != nullptr) {
-              const char* a = static_cast<const char*>(row) + (tile - warp) * S2T_W * k.code_bytes;   // the block's 256 sites
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
-            }
-          }
-        }
-        s2t_fetch_codes(ring[(size_t)(c1 & 1) * S2T_RING_OPS + o1], k.code_bytes, site, code_next);
-      }
+      const S2TImage& im = ring[o % RING];
+      s2t_cp_async_wait<1>();   // this op's codes have landed (the group of op o + 1 may still be in flight)
+      __syncwarp();
+      const unsigned char* codes = mycodes + (o % S2T_CODE_SLOTS) * (4 * S2T_W);
 
       double out[C][2];
-      int e_in = 0;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const int kind = im.kind[ch];
-        const double* pbase = &im.tab[ch][0];
-        const double2* pm = reinterpret_cast<const double2*>(pbase);
-#define CB_S2T_APPLY(L0, L1)                                            \
-  _Pragma("unroll") for (int c = 0; c < C; ++c) {                       \
-    _Pragma("unroll") for (int i = 0; i < 2; ++i) {                     \
-      const double2 pr = pm[c * 2 + i];                                  \
-      const double x = fma(pr.y, (L1), pr.x * (L0));                     \
-      if (ch == 0) out[c][i] = x; else out[c][i] *= x;                   \
-    }                                                                    \
-  }
-        if (kind == SRC_CARRIED) {
-          CB_S2T_APPLY(cur[c][0], cur[c][1])
-          e_in += cur_e;
-        } else if (kind == SRC_STACK) {
-          const double* sb = reinterpret_cast<const double*>(mybufs + (size_t)im.in_buf[ch] * TB) + lane;
-          double L[C][2];
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            L[c][0] = sb[(2 * c) * S2T_W];
-            L[c][1] = sb[(2 * c + 1) * S2T_W];
-          }
-          const int se = reinterpret_cast<const int*>(sb - lane + 2 * C * S2T_W)[lane];
-          CB_S2T_APPLY(L[c][0], L[c][1])
-          e_in += se;
-        } else if (kind == SRC_BUFFER) {
-          const double* gb = reinterpret_cast<const double*>(im.src[ch] + tile_off) + lane;
-          double L[C][2];
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            L[c][0] = __ldcg(gb + (2 * c) * S2T_W);
-            L[c][1] = __ldcg(gb + (2 * c + 1) * S2T_W);
-          }
-          const int se = __ldcg(reinterpret_cast<const int*>(gb - lane + 2 * C * S2T_W) + lane);
-          CB_S2T_APPLY(L[c][0], L[c][1])
-          e_in += se;
-        } else if (kind == SRC_TIP) {
-          const unsigned cd = min(code[ch][0], 2u);
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const double x = pbase[(c * 2 + i) * 4 + cd];
-              if (ch == 0) out[c][i] = x; else out[c][i] *= x;
-            }
-          }
-        } else {  // folded cherry: the pair of tip codes selects a precomputed row
-          const double* tab = pbase + (min(code[ch][0], 2u) * 3 + min(code[ch][1], 2u)) * (2 * C + 1);
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const double x = tab[c * 2 + i];
-              if (ch == 0) out[c][i] = x; else out[c][i] *= x;
-            }
-          }
-          e_in += (int)tab[2 * C];
-        }
-#undef CB_S2T_APPLY
+      int e_in;
+      switch (im.combo) {
+#define CB_S2T_CASE(NAME, K0, K1) \
+  case NAME: s2t_pair<C, K0, K1>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in); break;
+        CB_S2T_CASE(S2T_CARRIED_STACK, SRC_CARRIED, SRC_STACK)
+        CB_S2T_CASE(S2T_CARRIED_BUFFER, SRC_CARRIED, SRC_BUFFER)
+        CB_S2T_CASE(S2T_CARRIED_TIP, SRC_CARRIED, SRC_TIP)
+        CB_S2T_CASE(S2T_CARRIED_CHERRY, SRC_CARRIED, SRC_CHERRY)
+        CB_S2T_CASE(S2T_BUFFER_BUFFER, SRC_BUFFER, SRC_BUFFER)
+        CB_S2T_CASE(S2T_BUFFER_TIP, SRC_BUFFER, SRC_TIP)
+        CB_S2T_CASE(S2T_BUFFER_CHERRY, SRC_BUFFER, SRC_CHERRY)
+        CB_S2T_CASE(S2T_TIP_TIP, SRC_TIP, SRC_TIP)
+        CB_S2T_CASE(S2T_TIP_CHERRY, SRC_TIP, SRC_CHERRY)
+        default:
+          s2t_pair<C, SRC_CHERRY, SRC_CHERRY>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in);
+          break;
+#undef CB_S2T_CASE
       }
 
-      const bool is_root = im.is_root != 0;
-      int e_out = e_in;
-      if (!is_root) {
+      if (!im.is_root) {
+        // exact power-of-two rescale: all entries are >= 0, so the max of the high words carries the exponent of the max
         int mh = __double2hiint(out[0][0]);
 #pragma unroll
         for (int c = 0; c < C; ++c) mh = max(mh, max(__double2hiint(out[c][0]), __double2hiint(out[c][1])));
@@ -369,40 +434,7 @@ __global__ void __launch_bounds__(S2T_THREADS, 2) prune_s2t_kernel(const LaunchC
           cur[c][1] = out[c][1] * f;
         }
         cur_e = e_in + x;
-        e_out = cur_e;
-      }
-      // what gets written: the rescaled partial of an ordinary node, the partial as computed for an (optionally stored) root
-      char* const dst = im.dst;
-      const int ob = im.out_buf;
-      if (ob >= 0) {
-        if (groups_pending) {  // the bulk copy that last read this tile buffer is at least two groups old (host rule)
-          if (lane == 0) s2t_bulk_wait_read<1>();
-          __syncwarp();
-        }
-        double* sb = reinterpret_cast<double*>(mybufs + (size_t)ob * TB);
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          sb[(2 * c) * S2T_W + lane] = is_root ? out[c][0] : cur[c][0];
-          sb[(2 * c + 1) * S2T_W + lane] = is_root ? out[c][1] : cur[c][1];
-        }
-        reinterpret_cast<int*>(sb + 2 * C * S2T_W)[lane] = e_out;
-        if (dst != nullptr && !im.spill) {
-          s2t_fence_async_smem();
-          __syncwarp();
-          if (lane == 0) s2t_bulk_s2g(dst + tile_off, sb, TB);
-          groups_pending = true;
-        }  // (a pushed tile is popped by the lanes that wrote it: columns are lane-private, no barrier needed)
-      }
-      if (dst != nullptr && (ob < 0 || im.spill)) {  // plain coalesced stores (spills are re-read through the generic proxy)
-        double* gb = reinterpret_cast<double*>(dst + tile_off) + lane;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          __stcg(gb + (2 * c) * S2T_W, is_root ? out[c][0] : cur[c][0]);
-          __stcg(gb + (2 * c + 1) * S2T_W, is_root ? out[c][1] : cur[c][1]);
-        }
-        __stcg(reinterpret_cast<int*>(gb - lane + 2 * C * S2T_W) + lane, e_out);
-      }
-      if (is_root) {
+      } else {
         // ll_p = sum_c (pi . L_c) / n_cats ; lnL += w_p * log(ll_p)      ML_gamma.pyx:38,40
         const double pi0 = __ldg(k.pi), pi1 = __ldg(k.pi + 1);
         const double w = __ldg(k.weights + site);
@@ -411,17 +443,91 @@ __global__ void __launch_bounds__(S2T_THREADS, 2) prune_s2t_kernel(const LaunchC
 #pragma unroll
         for (int c = 0; c < C; ++c) s += fma(pi1, out[c][1], pi0 * out[c][0]) / k.cats;
         if (w != 0.0) lnl += w * (log(s) + (double)e_in * ln2);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {   // an (optionally) stored root partial is kept as computed, exponent e_in
+          cur[c][0] = out[c][0];
+          cur[c][1] = out[c][1];
+        }
+        cur_e = e_in;
       }
 
-      // leaving a chunk: the warp that finishes it last refills its ring half with the chunk two ahead
-      if (oc == S2T_RING_OPS - 1 && chunk + 2 < n_chunks) {
-        __syncwarp();
-        if (lane == 0) {
-          const int b = chunk & 1;
-          if (atomicAdd(&done_cnt[b], 1) == n_active - 1) {
-            done_cnt[b] = 0;
-            s2t_fence_async_smem();  // the warps' reads of this ring half before the async writes
-            issue_chunk(chunk + 2);
+      const int mode = im.store_mode;
+      if (mode != S2T_ST_NONE) {
+        if (mode & S2T_ST_GLOBAL) {  // plain coalesced stores: the tile is one contiguous 2 KB piece of the buffer
+          double* gb = reinterpret_cast<double*>(im.dst + tile_off);
+          if (mode & S2T_ST_STREAM) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              __stcs(gb + (2 * c) * S2T_W + lane, cur[c][0]);
+              __stcs(gb + (2 * c + 1) * S2T_W + lane, cur[c][1]);
+            }
+            __stcs(reinterpret_cast<int*>(gb + 2 * C * S2T_W) + lane, cur_e);
+          } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              __stcg(gb + (2 * c) * S2T_W + lane, cur[c][0]);
+              __stcg(gb + (2 * c + 1) * S2T_W + lane, cur[c][1]);
+            }
+            __stcg(reinterpret_cast<int*>(gb + 2 * C * S2T_W) + lane, cur_e);
+          }
+        }
+        if (mode & (S2T_ST_SMEM | S2T_ST_BULK)) {
+          if (groups_pending) {
+            // a staging buffer was last read by the bulk copy two groups ago; a stack slot may have been read by the
+            // latest group, so wait for all of them there
+            if (mode & S2T_ST_SMEM) s2t_bulk_wait_read<0>(); else s2t_bulk_wait_read<1>();
+            __syncwarp();
+          }
+          double* sb = reinterpret_cast<double*>(mybufs + (size_t)im.out_buf * TB);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            sb[(2 * c) * S2T_W + lane] = cur[c][0];
+            sb[(2 * c + 1) * S2T_W + lane] = cur[c][1];
+          }
+          reinterpret_cast<int*>(sb + 2 * C * S2T_W)[lane] = cur_e;
+          if (mode & S2T_ST_BULK) {
+            s2t_fence_async_smem();
+            __syncwarp();
+            if (lane == 0) s2t_bulk_s2g(im.dst + tile_off, sb, TB);
+            groups_pending = true;
+          }  // (a pushed tile is popped by the lanes that wrote it: columns are lane-private, no barrier needed)
+        }
+      }
+
+      // codes of op o + 2 (its image must be in the ring: entering a chunk also pulls the tips two chunks ahead to L2)
+      if (o + 2 < nops) {
+        if ((o + 2) % S2T_RING_OPS == 0) {
+          wait_chunk_of(o + 2);
+          const int c1 = (o + 2) / S2T_RING_OPS;
+          const int e = (c1 + 2) * S2T_RING_OPS + (lane >> 2);
+          if (lane < 4 * S2T_RING_OPS && e < nops && warp == c1 % n_active) {  // one warp per block and chunk does it
+            const OpDesc* __restrict__ dn = k.ops + rg.begin + e;
+            const int ch = (lane >> 1) & 1, t = lane & 1;
+            const int kind = dn->kind[ch];
+            const void* row = kind == SRC_TIP ? (t == 0 ? dn->src[ch] : nullptr) : (kind == SRC_CHERRY ? dn->ctip[ch][t] : nullptr);
+            if (row != nullptr) {
+              const char* a = static_cast<const char*>(row) + (tile - warp) * S2T_W;   // the block's 256 sites
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
+            }
+          }
+        }
+        issue_codes(o + 2);
+      }
+      s2t_cp_async_commit();
+
+      // leaving a chunk: the warp that finishes it last refills its ring stage with the chunk STAGES ahead
+      if ((o + 1) % S2T_RING_OPS == 0) {
+        const int chunk = o / S2T_RING_OPS;
+        if (chunk + S2T_RING_STAGES < n_chunks) {
+          __syncwarp();
+          if (lane == 0) {
+            const int b = chunk % S2T_RING_STAGES;
+            if (atomicAdd(&done_cnt[b], 1) == n_active - 1) {
+              done_cnt[b] = 0;
+              s2t_fence_async_smem();  // the warps' reads of this ring stage before the async writes
+              issue_chunk(chunk + S2T_RING_STAGES);
+            }
           }
         }
       }

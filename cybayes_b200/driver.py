@@ -37,6 +37,9 @@ READERS = {"bin": "readBinaryPhy", "multi": "readMultiPhy"}
 def load_alignment(input_file, data_type, reader=None):
     """Fill the config blackboard from a Phylip file (mat_mcmc_gamma.py:20-31)."""
     fn = getattr(utils, reader or READERS[data_type])
+    if config.LEAF_LLMAT is not None:      # a previous alignment of this process: free its device context
+        from . import likelihood
+        likelihood.drop_engine(config.LEAF_LLMAT)
     (config.N_TAXA, config.N_CHARS, config.ALPHABET, site_dict, config.LEAF_LLMAT, config.TAXA,
      config.N_SITES) = fn(input_file)
     config.IN_DTYPE = data_type
@@ -164,6 +167,7 @@ def run_chain(input_file, model, n_gen, thin, data_type, output_file, reader=Non
         tmats = state["transitionMat"]
         undo = []          # (category, edge, previous handle or None) to restore on rejection
         prop_tmats = None
+        proposed_cache = None   # a rejected proposal's partials go back to the pool before the next evaluation
         if param in ("pi", "rates"):
             new_param, hr = move(state[param].copy())
             if param == "pi":

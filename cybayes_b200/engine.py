@@ -250,5 +250,11 @@ class Engine(SlotPool):
     def sync(self):
         check(self._lib.cb_sync(self._ctx))
 
+    def fp64_peak_tflops(self):
+        """FP64 tensor-core peak of this GPU measured from registers (roofline denominator for S = 64)."""
+        out = np.zeros(1)
+        check(self._lib.cb_fp64_peak(self._ctx, _f64(out)))
+        return float(out[0])
+
     def flush_l2(self):
         check(self._lib.cb_flush_l2(self._ctx))

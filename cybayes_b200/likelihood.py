@@ -74,15 +74,25 @@ def engine_for(ll_mats, n_cats):
         # site-pattern sharding: this process (one per GPU) keeps a contiguous slice of the patterns; the
         # library all-reduces the scalar lnL over NCCL, so every rank sees the same number
         from .synthetic import shard_bounds
-        lo, hi = shard_bounds(codes.shape[1], rank, world, 64)
-        if hi <= lo:
-            raise ValueError(f"alignment has too few patterns ({codes.shape[1]}) to shard over {world} GPUs")
+        cuts = [shard_bounds(codes.shape[1], r, world, 64) for r in range(world)]
+        if any(h <= l for l, h in cuts):   # evaluated identically on every rank: all raise together, nobody is
+            raise ValueError(              # left waiting inside the communicator set-up
+                f"alignment has too few patterns ({codes.shape[1]}) to shard over {world} GPUs")
+        lo, hi = cuts[rank]
         codes = np.ascontiguousarray(codes[:, lo:hi])
         weights = None if weights is None else np.ascontiguousarray(weights[lo:hi])
         site_map = None  # per-site read-back of partials is a single-GPU debugging aid
     eng = _engine_factory(codes, S, n_cats, amb, weights)
     if world > 1:
-        eng.comm_init(_nccl_id(eng, rank, f"{S}x{n_cats}x{len(_engines)}"), rank, world)
+        global _comm_serial
+        _comm_serial += 1
+        uid, published = _nccl_id(eng, rank, f"{S}x{n_cats}x{_comm_serial}")
+        eng.comm_init(uid, rank, world)     # collective: when it returns on rank 0 every rank has read the id
+        if published is not None:
+            try:
+                os.remove(published)
+            except OSError:
+                pass
     _engines[key] = (ll_mats, eng, site_map)
     return eng, site_map
 
@@ -94,29 +104,49 @@ def _shard_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+_comm_serial = 0          # sharded contexts created by this process; never reset (reset_engines included)
+_PROCESS_START = None
+
+
 def _nccl_id(eng, rank, tag):
     """NCCL unique id made by rank 0 and handed to the other ranks through a file (no torch needed):
-    CYBAYES_NCCL_ID_DIR (default: the system temp dir) / cybayes_nccl_<MASTER_PORT>_<tag>.id"""
+    CYBAYES_NCCL_ID_DIR (default: the system temp dir) / cybayes_nccl_<MASTER_PORT>_<launcher pid>_<tag>.id
+    `tag` carries a per-process serial number, so two sharded alignments of one launch never share a name; readers
+    ignore a file older than their own process (left behind by a dead launch with a recycled pid / port), rank 0
+    removes such a file before it publishes and removes its own once every rank has joined (comm_init returns)."""
     import tempfile
     import time
+    global _PROCESS_START
+    if _PROCESS_START is None:
+        try:
+            import psutil
+            _PROCESS_START = psutil.Process().create_time()
+        except Exception:
+            _PROCESS_START = time.time() - 3600.0
     d = os.environ.get("CYBAYES_NCCL_ID_DIR", tempfile.gettempdir())
     # all ranks of one launch share the parent (the torchrun agent): its pid keeps launches apart
     path = os.path.join(d, f"cybayes_nccl_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_{tag}.id")
     if rank == 0:
-        import atexit
+        if os.path.exists(path):
+            os.remove(path)
         uid = eng.nccl_unique_id()
         with open(path + ".tmp", "wb") as fh:
             fh.write(uid)
         os.replace(path + ".tmp", path)
-        atexit.register(lambda: os.path.exists(path) and os.remove(path))
-        return uid
+        return uid, path
     t0 = time.time()
-    while not os.path.exists(path):
+    while True:
+        try:
+            if os.path.getmtime(path) >= _PROCESS_START - 2.0:
+                with open(path, "rb") as fh:
+                    uid = fh.read()
+                if len(uid) == 128:
+                    return uid, None
+        except OSError:
+            pass
         if time.time() - t0 > 120:
             raise TimeoutError(f"rank 0 never published {path}")
         time.sleep(0.01)
-    with open(path, "rb") as fh:
-        return fh.read()
 
 
 def _default_engine(n_cats=None):
@@ -126,6 +156,15 @@ def _default_engine(n_cats=None):
 
 
 subst._engine_hook = _default_engine
+
+
+def drop_engine(ll_mats):
+    """Free the device contexts holding `ll_mats` (a driver that loads another alignment)."""
+    for key in [k for k, v in _engines.items() if v[0] is ll_mats]:
+        try:
+            _engines.pop(key)[1].close()
+        except Exception:
+            pass
 
 
 def reset_engines():
@@ -198,33 +237,48 @@ def _plan_for(edges):
     return p
 
 
+def _gather_host_matrices(vals, n, S):
+    """(n, S, S) float64 array from n reference-style (S, S) ndarrays.  bytes.join walks the buffer protocol in C
+    (~60 ns per matrix against ~320 ns for np.concatenate) and refuses non-contiguous arrays; anything unusual
+    (other dtypes, views, nested lists) takes the general route."""
+    try:
+        if vals[0].dtype == np.float64 and vals[-1].dtype == np.float64:
+            buf = b"".join(vals)
+            if len(buf) == n * S * S * 8:
+                return np.frombuffer(buf, dtype=np.float64)
+    except (AttributeError, TypeError, BufferError, ValueError):
+        pass
+    mats = np.array([np.asarray(v, dtype=np.float64) for v in vals])
+    if mats.shape != (n, S, S):
+        raise ValueError(f"transition matrices must be {S} x {S}")
+    return mats
+
+
 def _slot_matrix(engine, tmats, edge_keys, getter=None):
-    """(n_edges, C) int32 P-slot table for the ops' edges.  Device tables are looked up; reference-style
-    host dicts of ndarrays are uploaded (host buffers -> one H2D copy per category) in op order."""
+    """(n_edges, C) int32 P-slot table for the ops' edges.  Device tables are looked up; reference-style host dicts
+    of ndarrays are gathered in op order and uploaded with ONE host -> device copy for all categories."""
     cols = []
     if getter is None:
         getter = itemgetter(*edge_keys) if len(edge_keys) > 1 else (lambda d: (d[edge_keys[0]],))
     keep = []
     n = len(edge_keys)
     S = engine.n_states
+    host = []   # (column index, matrices) of the host-side categories
     for t in tmats:
         if isinstance(t, PMatTable):
             if t.engine is not engine:
                 raise ValueError("transition matrices belong to a different alignment")
             cols.append(getter(t._slots))
             continue
-        vals = getter(t)
-        try:   # fastest way to gather thousands of small (S, S) arrays into one buffer
-            mats = np.concatenate(vals)
-            if mats.dtype != np.float64 or mats.shape != (n * S, S):
-                raise ValueError
-        except (ValueError, TypeError):
-            mats = np.array([np.asarray(v, dtype=np.float64) for v in vals])
-        block = engine.alloc_slots(n)
-        slots = np.arange(block.base, block.base + n, dtype=np.int32)
-        engine.upload_pmats(slots, mats)
+        host.append((len(cols), _gather_host_matrices(getter(t), n, S)))
+        cols.append(None)
+    if host:
+        block = engine.alloc_slots(n * len(host))
         keep.append(block)
-        cols.append(slots)
+        slots = np.arange(block.base, block.base + block.n, dtype=np.int32)
+        engine.upload_pmats(slots, host[0][1] if len(host) == 1 else np.concatenate([m.ravel() for _, m in host]))
+        for j, (col, _) in enumerate(host):
+            cols[col] = slots[j * n:(j + 1) * n]
     return np.ascontiguousarray(np.array(cols, dtype=np.int32).T), keep
 
 
@@ -241,7 +295,13 @@ class _CategoryView:
 
 class PartialCache:
     """Opaque snapshot of all internal-node partials on the device (the second return value of
-    matML / cache_matML).  ``cache[k][node]`` gives the reference's (S, n_sites) array."""
+    matML / cache_matML).  ``cache[k][node]`` gives the reference's (S, n_sites) array.
+
+    Deviations from the reference's list of dicts (ML_gamma.pyx:38-39), none visible to its drivers, which only
+    hand the cache back: the ROOT partial is not stored unless CYBAYES_STORE_ROOT=1 (the fused root kernel does not
+    need it; ``cache[k][root]`` raises otherwise); in site-sharded mode a rank only holds -- and returns -- its
+    own slice of the patterns; and matML divides by the number of tables passed (len(tmats)), which is what the
+    reference's drivers pass as n_cats."""
 
     def __init__(self, engine, snap, site_map, node_ids):
         self.engine, self.snap, self._site_map, self._nodes = engine, snap, site_map, node_ids

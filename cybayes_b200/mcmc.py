@@ -1,7 +1,8 @@
 """Mirror of the reference module ``mcmc`` (mcmc.pyx), the single-rate twin of ``mcmc_gamma``.
 
 Differences from mcmc_gamma that the reference has and that are kept:
-no node_slider / scale_alpha / GTR; rooted_NNI returns four values (mcmc.pyx:124);
+no scale_alpha / GTR (node_slider exists, mcmc.pyx:59-89, same as mcmc_gamma's; the non-Gamma driver just never
+proposes it); rooted_NNI returns four values (mcmc.pyx:124);
 mvDualSlider draws ``random.uniform(epsilon, sum)`` over ``range(config.N_CHARS)`` (:179-181);
 get_prob_t(pi, edges_dict, rates=None) has no rate argument (:427); get_edge_transition_mat
 mutates and returns the dict it is given (:354-378); state_init builds a single P dict.
@@ -13,8 +14,8 @@ from scipy.stats import dirichlet  # noqa: F401
 
 from . import config, moves, subst
 from .ML import cache_matML, matML  # noqa: F401
-from .moves import (bl_exp_scale, epsilon, externalSPR, init_pi_er, init_tree, newick2bl, rtree,  # noqa: F401
-                    scale_edge, scaler_alpha)
+from .moves import (bl_exp_scale, epsilon, externalSPR, init_pi_er, init_tree, newick2bl, node_slider,  # noqa: F401
+                    rtree, scale_edge, scaler_alpha)
 from .tree import (adjlist2newickBL, adjlist2nodes_dict, adjlist2reverse_nodes_dict, get_path2root,  # noqa: F401
                    postorder)
 

@@ -234,8 +234,9 @@ def get_prob_t_all(pi, edges_dict, rates, site_rates, n_cats=None):
     edges = list(edges_dict)
     n_e, n_c = len(edges), len(site_rates)
     block = engine.alloc_slots(n_e * n_c)
-    lengths = list(edges_dict.values())
-    d = np.array([v * r for r in site_rates for v in lengths], dtype=np.float64)
+    # d[k, e] = t_e * r_k, the product the reference forms per edge (mcmc_gamma.pyx:455,469,481): one rounding each
+    d = np.multiply.outer(np.array(site_rates, dtype=np.float64), np.fromiter(edges_dict.values(), dtype=np.float64,
+                                                                           count=n_e)).ravel()
     slots = np.arange(block.base, block.base + block.n, dtype=np.int32)
     _queue(engine, model, config.IN_DTYPE == "bin", pi, rates, slots, d, config.NORM_BETA)
     return [PMatTable(engine, edges, block, block.base + k * n_e, n_e) for k in range(n_c)]

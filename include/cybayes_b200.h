@@ -121,6 +121,53 @@ int cb_snapshot_release(cb_ctx* ctx, int snapshot);
  * in which case the scaling is folded back into out (may underflow, like the reference). */
 int cb_snapshot_read(cb_ctx* ctx, int snapshot, int node, double* out, int32_t* scale_out);
 
+/* ---- native generation loop -----------------------------------------------------------
+ * The Metropolis-Hastings loop of the reference driver (mat_mcmc_gamma.py:97-221) with its proposal generators
+ * (mcmc_gamma.pyx:40-198) run inside the library: cb_chain_run(n) performs n generations -- proposal, P matrices
+ * of the touched branches, dirty-path or full evaluation on the GPU, accept test -- without returning to the
+ * caller.  For a fixed seed it takes the reference's moves and decisions generation by generation: both random
+ * streams (Python `random`, NumPy legacy global generator: MT19937 states handed in and out) and the insertion
+ * order of the tree dict are reproduced.  The backend table lets a test replace the CUDA evaluation by callbacks;
+ * its last three members are host functions whose bits depend on SciPy / BLAS and are therefore always supplied
+ * by the caller (discrete-Gamma rates mcmc_gamma.pyx:596-602, beta = 1/(1 - pi.pi) :467, GTR eigensystem).     */
+typedef struct cb_chain cb_chain;
+typedef struct cb_chain_backend {
+  void* user;
+  /* NULL = the context's own cb_pmat_build / cb_eval / cb_snapshot_release */
+  int (*pmat_build)(void* user, int model, const double* pi, double beta, const double* gtr, int count,
+                    const int32_t* slots, const double* d, const double* x);
+  int (*eval)(void* user, int snapshot_in, int n_ops, const int32_t* nodes, const int32_t* children,
+              const int32_t* pslots, const double* pi, int flags, int* snapshot_out, double* lnl_out);
+  int (*snapshot_release)(void* user, int snapshot);
+  /* host maths, always required */
+  int (*site_rates)(void* user, double alpha, double* rates_out /* n_cats */);
+  int (*f81_beta)(void* user, const double* pi, int n_states, double* beta_out);
+  int (*gtr_eig)(void* user, const double* pi, const double* exchangeabilities, double* eig_out /* S + 2 S S */);
+} cb_chain_backend;
+/* model: 0 JC, 1 F81, 2 GTR.  param_ids[n_params] in the driver's order (0 pi, 1 rates, 2 tree, 3 bl, 4 srates)
+ * with their cumulative normalised weights; tree_cdf[2] = (NNI, eSPR), bl_cdf[2] = (scale_edge, node_slider)
+ * (mat_mcmc_gamma.py:65-84).  [slot_base, slot_base + slot_count) is a range of P slots the chain may use as it
+ * likes (>= 2 * n_edges * n_cats + 8 * n_cats).                                                                */
+int cb_chain_create(cb_ctx* ctx, const cb_chain_backend* backend, int n_taxa, int n_states, int n_cats, int model,
+                    int binary, int root, int slot_base, int slot_count, int host_exp_max, int n_params,
+                    const int32_t* param_ids, const double* params_cdf, const double* tree_cdf,
+                    const double* bl_cdf, cb_chain** chain_out);
+/* start state: tree edges in dict insertion order; builds every P matrix and runs the first full evaluation */
+int cb_chain_set_state(cb_chain* chain, int n_edges, const int32_t* parents, const int32_t* children,
+                       const double* lengths, const double* pi, int n_rates, const double* rates, double alpha,
+                       const double* site_rates, double beta, const double* gtr_eig, double* lnl_out);
+int cb_chain_set_rng(cb_chain* chain, const uint32_t* py_mt624, int py_pos, const uint32_t* np_mt624, int np_pos);
+int cb_chain_get_rng(cb_chain* chain, uint32_t* py_mt624, int* py_pos, uint32_t* np_mt624, int* np_pos);
+/* per-generation records (each array n_gens long, any may be NULL): move id (0 scale_edge, 1 node_slider,
+ * 2 rooted_NNI, 3 externalSPR, 4 mvDualSlider(pi), 5 scale_alpha, 6 mvDualSlider(rates)), accepted flag, lnL
+ * before, proposed lnL, log acceptance ratio, log u */
+int cb_chain_run(cb_chain* chain, int64_t n_gens, int8_t* move, int8_t* accepted, double* current_ll,
+                 double* proposed_ll, double* ll_ratio, double* log_u);
+int cb_chain_get_state(cb_chain* chain, int32_t* parents, int32_t* children, double* lengths, double* pi,
+                       double* rates, double* alpha, double* site_rates, double* lnl);
+int cb_chain_counters(cb_chain* chain, int64_t* moves7, int64_t* accepts7);
+int cb_chain_destroy(cb_chain* chain);
+
 /* ---- introspection / measurement ---------------------------------------------------------- */
 int cb_stats(cb_ctx* ctx, int64_t* kernel_launches, int64_t* bytes_h2d, int64_t* bytes_d2h,
              int64_t* device_bytes_in_use);
@@ -138,6 +185,8 @@ int cb_last_eval_info(cb_ctx* ctx, int64_t* bytes_written, int64_t* bytes_read, 
 int cb_mark(cb_ctx* ctx, int which);
 int cb_mark_elapsed_ms(cb_ctx* ctx, float* ms_out);
 int cb_sync(cb_ctx* ctx);
+/* bench helper: FP64 tensor-core (DMMA m8n8k4) peak of this GPU in TFLOP/s, measured from registers */
+int cb_fp64_peak(cb_ctx* ctx, double* tflops_out);
 /* bench helper: write 256 MB (> the 126 MB L2) to flush it */
 int cb_flush_l2(cb_ctx* ctx);
 

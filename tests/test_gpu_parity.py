@@ -357,22 +357,7 @@ def test_deep_tree_needs_scaling(gpu_backend):
     eng.close()
 
 
-TRACES = [("binary_F81", 300), ("twoStates_F81", 300), ("twoStates_JC", 300), ("narrow_F81", 3000),
-          ("narrow_JC", 500), ("broad_F81", 300), ("phon_ringe_JC", 500), ("phon_ringe_F81", 500),
-          ("phon_ringe_GTR", 300), ("ie42_JC", 200), ("ie42_GTR", 60)]
-
-
-def _compare_trace(rec, rows, meta, init_lnl, rel):
-    assert abs(init_lnl - meta["init_lnL"]) <= rel * abs(meta["init_lnL"])
-    assert len(rec) == len(rows)
-    for r, g in zip(rec, rows):
-        i, cur, prop, param, move = r[:5]
-        margin = f"first divergent generation {i}: got {r}, reference {g}"
-        assert str(param) == g["param"] and move == g["move"], margin
-        want = float(g["proposed_ll"])
-        if np.isfinite(want):
-            assert abs(prop - want) <= rel * abs(want), margin
-        assert abs(cur - float(g["current_ll"])) <= rel * abs(float(g["current_ll"])), margin
+from trace_checks import TRACES, check_outputs, compare_trace as _compare_trace  # noqa: E402
 
 
 @pytest.mark.parametrize("name,n_gen", TRACES)
@@ -388,14 +373,23 @@ def test_driver_trace_matches_reference(name, n_gen, golden_cases, gpu_backend, 
                     on_generation=lambda i, cur, prop, p, mv, acc, st: rec.append((i, cur, prop, p, mv, acc)))
     rel = REL_GTR if case["model"] == "GTR" else REL_CLOSED
     _compare_trace(rec, rows[:n_gen], meta, res["initial_lnL"], rel)
-    log_rows = open(str(tmp_path / "run.log")).read().splitlines()[1:]
-    for lr, g in zip(log_rows, rows):
-        f = lr.split("\t")
-        assert f[2] == g["log_TL"] and f[3] == g["alpha"]   # tree length and alpha: exact strings
-    trees = open(str(tmp_path / "run.trees")).read().strip().splitlines()
-    assert trees[-1].split("\t")[1] == meta["last_tree"]     # final sampled tree: exact Newick string
-    counters = sorted(f"({str(k[0])!r}, {k[1]!r}) {res['accepts'].get(k, 0)} {v}" for k, v in res["moves"].items())
-    assert counters == sorted(c.replace("np.str_(", "").replace("'),", "',", 1) for c in meta["counters"])
+    check_outputs(str(tmp_path / "run"), rows[:n_gen], meta, res)
+
+
+@pytest.mark.parametrize("name,n_gen", TRACES)
+def test_native_chain_trace_matches_reference(name, n_gen, golden_cases, gpu_backend, tmp_path):
+    """The same traces with the generation loop inside the library (cb_chain_*, csrc/mcmc_native.cuh): proposals, P
+    matrices, dirty-path evaluation and the accept test without returning to Python between generations."""
+    from cybayes_b200.fastchain import run_chain_native
+    case = golden_cases[name]
+    rows, meta = load_trace(name)
+    rec = []
+    res = run_chain_native(golden_io.data_path(case), case["model"], n_gen, 1, case["dtype"], str(tmp_path / "run"),
+                           out=io.StringIO(),
+                           on_generation=lambda i, cur, prop, p, mv, acc, st: rec.append((i, cur, prop, p, mv, acc)))
+    rel = REL_GTR if case["model"] == "GTR" else REL_CLOSED
+    _compare_trace(rec, rows[:n_gen], meta, res["initial_lnL"], rel)
+    check_outputs(str(tmp_path / "run"), rows[:n_gen], meta, res)
 
 
 def test_fast_spr_same_trace(golden_cases, gpu_backend, tmp_path):
@@ -509,13 +503,17 @@ def _c1_golden():
     return meta, z["move"], np.unpackbits(z["accepted"])[:len(z["move"])].astype(bool), z["proposed_ll_every_100"], log
 
 
-def test_c1_at_its_stated_length(golden_cases, gpu_backend, tmp_path):
+@pytest.mark.parametrize("runner", ["driver", "native"])
+def test_c1_at_its_stated_length(runner, golden_cases, gpu_backend, tmp_path):
     """Config C1 as the README runs it (README.md:46): narrow.phy, F81, -n 100000 -t 1000, seed 1234.  The restated
     driver on the CUDA engine must take the recorded move and make the recorded accept/reject decision in every one
     of the 100 000 generations (recorded from the unmodified reference, tests/golden/make_golden.py --c1-100k); on a
     mismatch the first divergent generation and the margin |ll_ratio - log u| of its acceptance test are reported
     (a rounding-level flip has a margin <~ 1e-9 * |lnL|)."""
-    from cybayes_b200.driver import run_chain
+    if runner == "driver":
+        from cybayes_b200.driver import run_chain
+    else:   # the same chain with the generation loop inside the library
+        from cybayes_b200.fastchain import run_chain_native as run_chain
     meta, move, accepted, sampled, log = _c1_golden()
     names = meta["moves"]
     n_gen = len(move)
@@ -550,7 +548,8 @@ def test_c1_at_its_stated_length(golden_cases, gpu_backend, tmp_path):
     assert hashlib.sha256(trees.encode()).hexdigest() == meta["trees_sha256"]
     counters = sorted(f"({str(k[0])!r}, {k[1]!r}) {res['accepts'].get(k, 0)} {v}" for k, v in res["moves"].items())
     assert counters == sorted(c.replace("np.str_(", "").replace("'),", "',", 1) for c in meta["counters"])
-    print(f"C1 100k: smallest acceptance margin over the run {margin.min():.3e} at generation {int(margin.argmin()) + 1}")
+    print(f"C1 100k ({runner}): {res['gens_per_sec']:.0f} generations/s; smallest acceptance margin over the run "
+          f"{margin.min():.3e} at generation {int(margin.argmin()) + 1}")
 
 
 def test_c1_at_its_stated_length_unmodified_script(gpu_backend, tmp_path, monkeypatch, capsys):
@@ -573,14 +572,17 @@ def test_c1_at_its_stated_length_unmodified_script(gpu_backend, tmp_path, monkey
     assert sorted(counters) == sorted(meta["counters"])
 
 
-@pytest.mark.parametrize("n_taxa,n_sites,model,slots,n_cats", [(2, 70, "F81", 3, 4), (12, 333, "F81", 3, 4),
-                                                               (40, 1000, "GTR", 1, 4), (64, 3000, "GTR", 0, 4),
-                                                               (33, 257, "F81", 2, 4), (200, 640, "GTR", 3, 4),
-                                                               (25, 500, "F81", 3, 1), (90, 2100, "GTR", 2, 1)])
-def test_tiled_two_state_kernel_small_inputs(n_taxa, n_sites, model, slots, n_cats, gpu_backend, monkeypatch):
-    """The large-alignment 2-state kernel (kernels_s2t.cuh: tile-interleaved partials, shared-memory stack, bulk-async
-    stores, op images) forced onto small inputs: ragged last blocks, 0-3 stack slots (spills through global memory),
-    every schedule, dirty paths and batches -- and bit-identical partials to the row-major kernel."""
+@pytest.mark.parametrize("n_taxa,n_sites,model,slots,n_cats,minb,bulk",
+                         [(2, 70, "F81", 3, 4, 2, 0), (12, 333, "F81", 3, 4, 3, 0), (40, 1000, "GTR", 1, 4, 2, 1),
+                          (64, 3000, "GTR", 0, 4, 3, 0), (33, 257, "F81", 2, 4, 2, 0), (200, 640, "GTR", 4, 4, 2, 0),
+                          (200, 640, "GTR", 3, 4, 3, 1), (25, 500, "F81", 3, 1, 2, 0), (90, 2100, "GTR", 2, 1, 3, 1)])
+def test_tiled_two_state_kernel_small_inputs(n_taxa, n_sites, model, slots, n_cats, minb, bulk, gpu_backend, monkeypatch):
+    """The large-alignment 2-state kernel (kernels_s2t.cuh: tile-interleaved partials, shared-memory stack, op images,
+    cp.async code ring) forced onto small inputs: ragged last blocks, 0-4 stack slots (spills through global memory),
+    both occupancy variants, plain and bulk-async stores, every schedule, dirty paths and batches -- and bit-identical
+    partials to the row-major kernel."""
+    monkeypatch.setenv("CYBAYES_S2T_MINB", str(minb))
+    monkeypatch.setenv("CYBAYES_S2T_BULK", str(bulk))
     from cybayes_b200.engine import Engine
     from cybayes_b200.likelihood import _Plan
     monkeypatch.setenv("CYBAYES_S2_TILED", "1")
