@@ -14,8 +14,37 @@ c_i32p = C.POINTER(C.c_int32)
 c_f64p = C.POINTER(C.c_double)
 c_i64p = C.POINTER(C.c_int64)
 
+c_u32p = C.POINTER(C.c_uint32)
+c_i8p = C.POINTER(C.c_int8)
+
+# cb_chain_backend (native generation loop): callback table
+CHAIN_BUILD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_f64p, C.c_double, c_f64p, C.c_int, c_i32p, c_f64p, c_f64p)
+CHAIN_EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p, c_f64p, C.c_int,
+                            C.POINTER(C.c_int), c_f64p)
+CHAIN_RELEASE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)
+CHAIN_RATES_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_double, c_f64p)
+CHAIN_BETA_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, c_f64p, C.c_int, c_f64p)
+CHAIN_EIG_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, c_f64p, c_f64p, c_f64p)
+
+
+class ChainBackend(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("pmat_build", CHAIN_BUILD_FN), ("eval", CHAIN_EVAL_FN),
+                ("snapshot_release", CHAIN_RELEASE_FN), ("site_rates", CHAIN_RATES_FN), ("f81_beta", CHAIN_BETA_FN),
+                ("gtr_eig", CHAIN_EIG_FN)]
+
+
 # name -> (restype, argtypes); mirrors include/cybayes_b200.h one to one
 SIGNATURES = {
+    "cb_chain_create": (C.c_int, [C.c_void_p, C.POINTER(ChainBackend)] + [C.c_int] * 10 +
+                        [c_i32p, c_f64p, c_f64p, c_f64p, C.POINTER(C.c_void_p)]),
+    "cb_chain_set_state": (C.c_int, [C.c_void_p, C.c_int, c_i32p, c_i32p, c_f64p, c_f64p, C.c_int, c_f64p, C.c_double,
+                                     c_f64p, C.c_double, c_f64p, c_f64p]),
+    "cb_chain_set_rng": (C.c_int, [C.c_void_p, c_u32p, C.c_int, c_u32p, C.c_int]),
+    "cb_chain_get_rng": (C.c_int, [C.c_void_p, c_u32p, C.POINTER(C.c_int), c_u32p, C.POINTER(C.c_int)]),
+    "cb_chain_run": (C.c_int, [C.c_void_p, C.c_int64, c_i8p, c_i8p, c_f64p, c_f64p, c_f64p, c_f64p]),
+    "cb_chain_get_state": (C.c_int, [C.c_void_p, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p]),
+    "cb_chain_counters": (C.c_int, [C.c_void_p, c_i64p, c_i64p]),
+    "cb_chain_destroy": (C.c_int, [C.c_void_p]),
     "cb_last_error": (C.c_char_p, []),
     "cb_version": (C.c_int, []),
     "cb_device_count": (C.c_int, [C.POINTER(C.c_int)]),

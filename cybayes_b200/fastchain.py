@@ -29,40 +29,9 @@ MOVES = [("bl", "scale_edge"), ("bl", "node_slider"), ("tree", "rooted_NNI"), ("
 PARAM_IDS = {"pi": 0, "rates": 1, "tree": 2, "bl": 3, "srates": 4}
 MODEL_IDS = {"JC": 0, "F81": 1, "GTR": 2}
 
-_BUILD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_f64p, C.c_double, c_f64p, C.c_int, c_i32p, c_f64p, c_f64p)
-_EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p, c_f64p, C.c_int, C.POINTER(C.c_int),
-                       c_f64p)
-_RELEASE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)
-_RATES_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_double, c_f64p)
-_BETA_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, c_f64p, C.c_int, c_f64p)
-_EIG_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, c_f64p, c_f64p, c_f64p)
-
-
-class ChainBackend(C.Structure):
-    _fields_ = [("user", C.c_void_p), ("pmat_build", _BUILD_FN), ("eval", _EVAL_FN), ("snapshot_release", _RELEASE_FN),
-                ("site_rates", _RATES_FN), ("f81_beta", _BETA_FN), ("gtr_eig", _EIG_FN)]
-
-
-def _declare(lib):
-    if getattr(lib, "_chain_declared", False):
-        return
-    vp, i64p = C.c_void_p, C.POINTER(C.c_int64)
-    u32p, i8p = C.POINTER(C.c_uint32), C.POINTER(C.c_int8)
-    sig = {
-        "cb_chain_create": [vp, C.POINTER(ChainBackend)] + [C.c_int] * 10 + [c_i32p, c_f64p, c_f64p, c_f64p, C.POINTER(vp)],
-        "cb_chain_set_state": [vp, C.c_int, c_i32p, c_i32p, c_f64p, c_f64p, C.c_int, c_f64p, C.c_double, c_f64p, C.c_double,
-                               c_f64p, c_f64p],
-        "cb_chain_set_rng": [vp, u32p, C.c_int, u32p, C.c_int],
-        "cb_chain_get_rng": [vp, u32p, C.POINTER(C.c_int), u32p, C.POINTER(C.c_int)],
-        "cb_chain_run": [vp, C.c_int64, i8p, i8p, c_f64p, c_f64p, c_f64p, c_f64p],
-        "cb_chain_get_state": [vp, c_i32p, c_i32p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p],
-        "cb_chain_counters": [vp, i64p, i64p],
-        "cb_chain_destroy": [vp],
-    }
-    for name, args in sig.items():
-        fn = getattr(lib, name)
-        fn.restype, fn.argtypes = C.c_int, args
-    lib._chain_declared = True
+_BUILD_FN, _EVAL_FN, _RELEASE_FN = _lib.CHAIN_BUILD_FN, _lib.CHAIN_EVAL_FN, _lib.CHAIN_RELEASE_FN
+_RATES_FN, _BETA_FN, _EIG_FN = _lib.CHAIN_RATES_FN, _lib.CHAIN_BETA_FN, _lib.CHAIN_EIG_FN
+ChainBackend = _lib.ChainBackend
 
 
 def _host_callbacks(n_states, n_cats, n_rates):
@@ -137,7 +106,6 @@ class NativeChain:
 
     def __init__(self, engine, state, site_rates, model, binary, use_callbacks=False):
         lib = _lib.load()
-        _declare(lib)
         self._lib, self.engine = lib, engine
         self.n_taxa, self.n_states, self.n_cats = config.N_TAXA, engine.n_states, engine.n_cats
         tree = state["tree"]
