@@ -66,6 +66,7 @@ SIGNATURES = {
     "cb_snapshot_release": (C.c_int, [C.c_void_p, C.c_int]),
     "cb_snapshot_read": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_f64p, c_i32p]),
     "cb_stats": (C.c_int, [C.c_void_p, c_i64p, c_i64p, c_i64p, c_i64p]),
+    "cb_mem_info": (C.c_int, [C.c_void_p, c_i64p, c_i64p, c_i64p, c_i64p]),
     "cb_last_eval_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cb_last_eval_main_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cb_last_eval_info": (C.c_int, [C.c_void_p, c_i64p, c_i64p, c_i32p]),

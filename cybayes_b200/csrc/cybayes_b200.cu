@@ -223,12 +223,25 @@ struct cb_ctx {
   int64_t last_bytes_written = 0, last_bytes_read = 0;
   int32_t last_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // stats
-  int64_t launches = 0, h2d = 0, d2h = 0, dev_bytes = 0;
+  int64_t launches = 0, h2d = 0, d2h = 0, dev_bytes = 0, max_dev_bytes = 0;
   bool timing_valid = false;
 };
 
 static int dev_alloc(cb_ctx* c, void** p, size_t bytes) {
-  CU(cudaMalloc(p, bytes));
+  // CYBAYES_MAX_DEVICE_BYTES caps what one context may hold (a share of a GPU; also how the tests reach this path)
+  cudaError_t e = (c->max_dev_bytes > 0 && c->dev_bytes + (int64_t)bytes > c->max_dev_bytes) ? cudaErrorMemoryAllocation
+                                                                                              : cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();  // not sticky: clear it
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    return fail("out of device memory: %.2f GB requested with %.2f GB in use by this context (%.2f GB free on the GPU%s). "
+                "The partial cache of this alignment needs about %.1f GB: shard the patterns over more GPUs (CYBAYES_SHARD=1 "
+                "under torchrun) or evaluate without keeping the cache",
+                bytes / 1e9, c->dev_bytes / 1e9, fr / 1e9, c->max_dev_bytes > 0 ? ", context capped by CYBAYES_MAX_DEVICE_BYTES" : "",
+                (double)c->buffer_bytes * std::max(0, c->n_taxa - 2) / 1e9);
+  }
+  if (e != cudaSuccess) return fail("%s:%d cudaMalloc: %s", __FILE__, __LINE__, cudaGetErrorString(e));
   c->dev_bytes += (int64_t)bytes;
   return 0;
 }
@@ -280,6 +293,7 @@ static int create_impl(int device, cb_ctx** out) {
   c->s2t_slots = c->s2t_minb == 3 ? 3 : 4;
   if (const char* v = getenv("CYBAYES_S2T_SLOTS")) c->s2t_slots = std::max(0, std::min(8, atoi(v)));
   if (getenv("CYBAYES_NO_PLAN_CACHE")) c->no_plan_cache = true;
+  if (const char* v = getenv("CYBAYES_MAX_DEVICE_BYTES")) c->max_dev_bytes = atoll(v);
 #define CB_S2T_ATTR(CC, MB) CU(cudaFuncSetAttribute(prune_s2t_kernel<CC, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024))
   CB_S2T_ATTR(4, 2); CB_S2T_ATTR(4, 3); CB_S2T_ATTR(1, 2); CB_S2T_ATTR(1, 3);   // + 384 B static each
 #undef CB_S2T_ATTR
@@ -1612,6 +1626,21 @@ extern "C" int cb_stats(cb_ctx* c, int64_t* launches, int64_t* h2d, int64_t* d2h
   if (h2d) *h2d = c->h2d;
   if (d2h) *d2h = c->d2h;
   if (dev_bytes) *dev_bytes = c->dev_bytes;
+  return 0;
+}
+extern "C" int cb_mem_info(cb_ctx* c, int64_t* free_bytes, int64_t* total_bytes, int64_t* pooled_bytes, int64_t* partial_bytes) {
+  REQUIRE(c, "null argument");
+  CU(cudaSetDevice(c->device));
+  size_t fr = 0, tot = 0;
+  CU(cudaMemGetInfo(&fr, &tot));
+  if (c->max_dev_bytes > 0) {  // a capped context sees its cap
+    tot = (size_t)c->max_dev_bytes;
+    fr = (size_t)std::max<int64_t>(0, std::min<int64_t>((int64_t)fr, c->max_dev_bytes - c->dev_bytes));
+  }
+  if (free_bytes) *free_bytes = (int64_t)fr;
+  if (total_bytes) *total_bytes = (int64_t)tot;
+  if (pooled_bytes) *pooled_bytes = (int64_t)c->free_buffers.size() * (int64_t)c->buffer_bytes;
+  if (partial_bytes) *partial_bytes = (int64_t)c->buffer_bytes;
   return 0;
 }
 extern "C" int cb_last_eval_ms(cb_ctx* c, float* ms) {

@@ -218,6 +218,13 @@ class Engine(SlotPool):
         return {"kernel_launches": v[0].value, "h2d_bytes": v[1].value, "d2h_bytes": v[2].value,
                 "device_bytes": v[3].value}
 
+    def mem_info(self):
+        """Device memory as the context sees it: free / total bytes, bytes pooled in unused partial buffers, bytes of
+        one partial buffer."""
+        x = [C.c_int64() for _ in range(4)]
+        check(self._lib.cb_mem_info(self._ctx, *[C.byref(t) for t in x]))
+        return {"free": x[0].value, "total": x[1].value, "pooled": x[2].value, "partial": x[3].value}
+
     def last_eval_ms(self):
         ms = C.c_float()
         check(self._lib.cb_last_eval_ms(self._ctx, C.byref(ms)))

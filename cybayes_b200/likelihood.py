@@ -342,6 +342,24 @@ STORE_ROOT = os.environ.get("CYBAYES_STORE_ROOT", "0") == "1"
 LAZY_CACHE_MIN_SITES = int(os.environ.get("CYBAYES_LAZY_CACHE_MIN_SITES", str(1 << 62)))
 
 
+CACHE_CHECK_MIN_BYTES = 1 << 30
+
+
+def _cache_fits(engine, n_nodes):
+    """Can this context hold one more full cache (one partial buffer per stored node) next to what it already has?
+    Only asked when the cache is big enough to matter (> 1 GB); the margin covers temporaries of later dirty paths.
+    C5 on one B200 (209 GB of partials) does not fit: matML then evaluates the likelihood without keeping partials
+    and returns a LazyPartialCache that materialises on first use -- or fails there with a clear out-of-memory message."""
+    mem = getattr(engine, "mem_info", None)
+    if mem is None:
+        return True
+    info = mem()
+    need = (n_nodes - 1) * info["partial"]
+    if need < CACHE_CHECK_MIN_BYTES:
+        return True
+    return need <= 0.92 * (info["free"] + info["pooled"])
+
+
 class LazyPartialCache(PartialCache):
     """Cache of a full pass whose partials are only materialised (by re-running the pass with
     stores) when first needed.  Holds what that needs: the op list, the P slots (kept alive through
@@ -375,7 +393,7 @@ def _full(pi, root, ll_mats, edges, tmats, n_cats_tables):
         raise KeyError(root)
     pslots, keep = _slot_matrix(engine, tmats, plan.edge_keys)
     nodes = plan.nodes if STORE_ROOT else plan.nodes[:-1]
-    if engine.n_patterns >= LAZY_CACHE_MIN_SITES:
+    if engine.n_patterns >= LAZY_CACHE_MIN_SITES or not _cache_fits(engine, len(plan.nodes)):
         lnl, _ = engine.eval(None, plan.nodes, plan.children, pslots, np.asarray(pi, dtype=np.float64),
                              want_snapshot=False)
         alive = keep + [t._block for t in tmats if isinstance(t, PMatTable)] + \

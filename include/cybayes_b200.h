@@ -171,6 +171,10 @@ int cb_chain_destroy(cb_chain* chain);
 /* ---- introspection / measurement ---------------------------------------------------------- */
 int cb_stats(cb_ctx* ctx, int64_t* kernel_launches, int64_t* bytes_h2d, int64_t* bytes_d2h,
              int64_t* device_bytes_in_use);
+/* device memory: free / total bytes on the GPU (or under CYBAYES_MAX_DEVICE_BYTES), bytes of partial buffers sitting
+ * unused in the context's pool, bytes of one partial buffer -- what the caller needs to decide whether the cache
+ * of a full evaluation fits (C5's 209 GB cache does not fit one GPU) */
+int cb_mem_info(cb_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes, int64_t* pooled_bytes, int64_t* partial_bytes);
 /* device time in ms of the kernels of the last synchronous cb_eval / cb_eval_batch
  * (CUDA events on the launching stream) */
 int cb_last_eval_ms(cb_ctx* ctx, float* ms_out);

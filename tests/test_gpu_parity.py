@@ -656,3 +656,45 @@ def test_batched_spr_scoring(name, golden_cases, gpu_backend):
                 for r in site_rates]
         want = oracle.mat_ml(pi, root, ll, proposals[idx][1], tm_o, n_sites, N)[0]
         assert abs(batch[idx] - want) <= rel * abs(want), (idx, batch[idx], want)
+
+
+def test_cache_that_does_not_fit_is_lazy_and_fails_cleanly(gpu_backend, monkeypatch):
+    """SURVEY 7 / C5 on one GPU: when the partial cache of a full evaluation cannot fit the device, matML evaluates the
+    likelihood without keeping partials and hands back a lazy cache; using that cache then fails with a clear
+    out-of-memory error instead of a raw cudaMalloc failure.  Reached here with a per-context memory cap."""
+    from cybayes_b200 import config
+    from cybayes_b200._lib import CyBayesB200Error
+    from cybayes_b200.alignment import LeafMatrices
+    from cybayes_b200.likelihood import LazyPartialCache
+    from cybayes_b200.ML_gamma import cache_matML, matML
+    from cybayes_b200.mcmc_gamma import get_prob_t
+    from cybayes_b200.synthetic import SyntheticAlignment
+    N, P = 64, 81920     # >= 75 776 patterns: the tiled kernel, whose walk keeps read-backs on chip
+    aln = SyntheticAlignment(N, P, 2, 77, block_sites=2048)
+    codes = aln.codes(0, P)
+    monkeypatch.setattr(gpu_backend, "COMPRESS_MAX_SITES", 0)
+    monkeypatch.setattr(gpu_backend, "CACHE_CHECK_MIN_BYTES", 0)
+    config.N_TAXA, config.N_CHARS, config.N_SITES, config.MODEL, config.IN_DTYPE, config.N_CATS = N, 2, P, "GTR", "bin", 4
+    edges = aln.edge_order()
+
+    def evaluate():
+        leaves = LeafMatrices(codes, 2, np.ones((1, 2)))
+        config.LEAF_LLMAT = leaves
+        tabs = [get_prob_t(aln.pi, aln.tree, aln.er, r) for r in aln.rates]
+        return leaves, tabs, matML(aln.pi, aln.root, leaves, edges, tabs, P, N, 4)
+    _, _, (want, cache) = evaluate()
+    assert not isinstance(cache, LazyPartialCache)
+    del cache
+    gpu_backend.reset_engines()
+    # one partial buffer is 81920 * 68 B = 5.6 MB, the full cache up to 62 of them: cap the context at 64 MB
+    monkeypatch.setenv("CYBAYES_MAX_DEVICE_BYTES", str(64 << 20))
+    leaves, tabs, (lnl, cache) = evaluate()
+    assert lnl == want
+    assert isinstance(cache, LazyPartialCache)
+    parents = oracle.parent_of(aln.tree)
+    path = oracle.path_to_root(parents, 5, aln.root)
+    with pytest.raises(CyBayesB200Error, match="out of device memory.*shard the patterns"):
+        cache_matML(aln.pi, aln.root, leaves, cache, path, edges, tabs, P, N, 4)
+    # the context survives the failure (everything the failed evaluation had acquired went back to the pool)
+    l2, c2 = matML(aln.pi, aln.root, leaves, edges, tabs, P, N, 4)
+    assert l2 == want and isinstance(c2, LazyPartialCache)
