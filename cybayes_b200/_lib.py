@@ -54,6 +54,7 @@ SIGNATURES = {
     "cb_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "cb_set_tips": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int,
                               c_f64p, C.c_int, c_f64p]),
+    "cb_compress_patterns": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int, c_i64p, c_i64p, c_f64p, c_i64p]),
     "cb_pmat_reserve": (C.c_int, [C.c_void_p, C.c_int]),
     "cb_pmat_upload": (C.c_int, [C.c_void_p, C.c_int, c_i32p, c_f64p]),
     "cb_pmat_download": (C.c_int, [C.c_void_p, C.c_int, c_i32p, c_f64p]),

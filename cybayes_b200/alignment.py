@@ -216,3 +216,26 @@ def compress_patterns(codes):
     rank[order] = np.arange(order.size)
     pattern_codes = np.ascontiguousarray(cols[first[order]].T)
     return pattern_codes, counts[order].astype(np.float64), rank[inverse.ravel()]
+
+
+def compress_patterns_gpu(codes, device=None):
+    """compress_patterns for alignments too long for the host route (10^5 .. 10^7 columns): the column comparison runs
+    on the GPU (cb_compress_patterns: 128-bit column hashes, verified column by column, so the result is exact).
+    Same return value as compress_patterns, element for element."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    codes = np.ascontiguousarray(codes)
+    n_taxa, n_sites = codes.shape
+    if device is None:
+        device = int(os.environ.get("CYBAYES_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    site_to_pattern = np.empty(n_sites, dtype=np.int64)
+    first = np.empty(n_sites, dtype=np.int64)
+    weights = np.empty(n_sites, dtype=np.float64)
+    n_pat = C.c_int64()
+    _lib.check(lib.cb_compress_patterns(int(device), codes.ctypes.data_as(C.c_void_p), n_taxa, n_sites, codes.dtype.itemsize,
+                                        site_to_pattern.ctypes.data_as(_lib.c_i64p), first.ctypes.data_as(_lib.c_i64p),
+                                        weights.ctypes.data_as(_lib.c_f64p), C.byref(n_pat)))
+    n = n_pat.value
+    return np.ascontiguousarray(codes[:, first[:n]]), weights[:n].copy(), site_to_pattern

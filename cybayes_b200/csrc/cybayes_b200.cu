@@ -189,12 +189,14 @@ struct cb_ctx {
   double* d_pmats_lib = nullptr;
   int lib_cap = 0;  // records the library pool can hold
   // staging
-  OpDesc* h_ops = nullptr;
-  OpDesc* d_ops = nullptr;
-  int ops_cap = 0;
-  RangeDesc* h_ranges = nullptr;
-  RangeDesc* d_ranges = nullptr;
-  int ranges_cap = 0;
+  // one pinned block + its device mirror per evaluation: [ops][ranges][pi], uploaded with ONE copy
+  unsigned char* h_stage = nullptr;
+  unsigned char* d_stage = nullptr;
+  size_t stage_cap = 0;
+  int images_cap = 0;  // op images (tiled 2-state kernel), in ops
+  cudaEvent_t ev_scratch = nullptr;  // the last host -> device copy out of h_scratch has finished
+  bool timing = true;                // record the per-evaluation timing events (the native chain switches them off)
+  bool results_mapped = false;       // h_results is mapped: the root kernel writes lnL straight into host memory
   double* d_block_sums = nullptr;
   unsigned* d_tickets = nullptr;
   double* d_results = nullptr;
@@ -227,6 +229,7 @@ struct cb_ctx {
   bool timing_valid = false;
 };
 
+static void dev_account(int device, int64_t delta);
 static int dev_alloc(cb_ctx* c, void** p, size_t bytes) {
   // CYBAYES_MAX_DEVICE_BYTES caps what one context may hold (a share of a GPU; also how the tests reach this path)
   cudaError_t e = (c->max_dev_bytes > 0 && c->dev_bytes + (int64_t)bytes > c->max_dev_bytes) ? cudaErrorMemoryAllocation
@@ -243,12 +246,14 @@ static int dev_alloc(cb_ctx* c, void** p, size_t bytes) {
   }
   if (e != cudaSuccess) return fail("%s:%d cudaMalloc: %s", __FILE__, __LINE__, cudaGetErrorString(e));
   c->dev_bytes += (int64_t)bytes;
+  dev_account(c->device, (int64_t)bytes);
   return 0;
 }
 static void dev_free(cb_ctx* c, void* p, size_t bytes) {
   if (p) {
     cudaFree(p);
     c->dev_bytes -= (int64_t)bytes;
+    dev_account(c->device, -(int64_t)bytes);
   }
 }
 
@@ -280,6 +285,7 @@ static int create_impl(int device, cb_ctx** out) {
   CU(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev_mark[0]));
   CU(cudaEventCreate(&c->ev_mark[1]));
+  CU(cudaEventCreateWithFlags(&c->ev_scratch, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev_main0));
   CU(cudaEventCreate(&c->ev_main1));
   cudaDeviceProp prop;
@@ -313,13 +319,9 @@ static int create_impl(int device, cb_ctx** out) {
 
 static void free_alignment(cb_ctx* c) {
   c->plans.clear();
-  if (c->d_images) {  // sized with the op staging area: both are re-created on demand
-    dev_free(c, c->d_images, (size_t)c->ops_cap * sizeof(S2TImage));
-    c->d_images = nullptr;
-    if (c->d_ops) dev_free(c, c->d_ops, (size_t)c->ops_cap * sizeof(OpDesc));
-    if (c->h_ops) cudaFreeHost(c->h_ops);
-    c->d_ops = nullptr; c->h_ops = nullptr; c->ops_cap = 0;
-  }
+  if (c->d_images) dev_free(c, c->d_images, (size_t)c->images_cap * sizeof(S2TImage));
+  c->d_images = nullptr;
+  c->images_cap = 0;
   for (auto& b : c->buffers) dev_free(c, b.data, c->buffer_bytes);
   c->buffers.clear();
   c->free_buffers.clear();
@@ -360,11 +362,9 @@ extern "C" int cb_destroy(cb_ctx* c) {
   cudaStreamSynchronize(c->stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   free_alignment(c);
-  if (c->d_ops) dev_free(c, c->d_ops, (size_t)c->ops_cap * sizeof(OpDesc));
-  if (c->d_images) dev_free(c, c->d_images, (size_t)c->ops_cap * sizeof(S2TImage));
-  if (c->d_ranges) dev_free(c, c->d_ranges, (size_t)c->ranges_cap * sizeof(RangeDesc));
-  if (c->h_ops) cudaFreeHost(c->h_ops);
-  if (c->h_ranges) cudaFreeHost(c->h_ranges);
+  if (c->d_stage) dev_free(c, c->d_stage, c->stage_cap);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->ev_scratch) cudaEventDestroy(c->ev_scratch);
   if (c->d_scratch) dev_free(c, c->d_scratch, c->scratch_cap);
   if (c->h_scratch) cudaFreeHost(c->h_scratch);
   if (c->d_flush) dev_free(c, c->d_flush, c->flush_bytes);
@@ -450,11 +450,6 @@ static int set_tips_impl(cb_ctx* c, int n_taxa, int64_t n_sites, int n_states, i
     // large binary alignments use the tiled kernel (kernels_s2t.cuh); CYBAYES_S2_TILED=1/0 forces it on / off (tests)
     const char* v = getenv("CYBAYES_S2_TILED");
     c->s2_tiled = c->family_s2 && code_bytes == 1 && (v ? atoi(v) != 0 : c->P >= S2_TILED_MIN_SITES);
-    if (c->s2_tiled && c->ops_cap > 0 && !c->d_images) {  // staging sized before this alignment: re-create it with images
-      if (c->d_ops) dev_free(c, c->d_ops, (size_t)c->ops_cap * sizeof(OpDesc));
-      if (c->h_ops) cudaFreeHost(c->h_ops);
-      c->d_ops = nullptr; c->h_ops = nullptr; c->ops_cap = 0;
-    }
   }
   c->use_dmma = !c->family_s2 && n_states >= 32 && n_states <= 64 && !getenv("CYBAYES_NO_DMMA");
   {
@@ -533,7 +528,7 @@ extern "C" int cb_pmat_upload(cb_ctx* c, int count, const int32_t* slots, const 
   CU(cudaSetDevice(c->device));
   const size_t mat = (size_t)c->n_states * c->n_states * 8;
   if (ensure_scratch(c, (size_t)count * mat)) return 1;
-  CU(cudaStreamSynchronize(c->stream));  // scratch reuse
+  CU(cudaEventSynchronize(c->ev_scratch));  // the previous copy out of the pinned scratch has finished
   memcpy(c->h_scratch, mats, (size_t)count * mat);
   int i = 0;
   while (i < count) {  // coalesce runs of consecutive slots into one copy
@@ -543,6 +538,7 @@ extern "C" int cb_pmat_upload(cb_ctx* c, int count, const int32_t* slots, const 
                        (size_t)(j - i) * mat, cudaMemcpyHostToDevice, c->stream));
     i = j;
   }
+  CU(cudaEventRecord(c->ev_scratch, c->stream));
   c->h2d += (int64_t)count * mat;
   return 0;
 }
@@ -576,7 +572,7 @@ extern "C" int cb_pmat_build(cb_ctx* c, int model, const double* pi, double beta
   const size_t doubles = (size_t)S + n_gtr + 2 * (size_t)count;
   const size_t bytes = doubles * 8 + (size_t)count * 4;
   if (ensure_scratch(c, bytes)) return 1;
-  CU(cudaStreamSynchronize(c->stream));  // scratch reuse
+  CU(cudaEventSynchronize(c->ev_scratch));  // the previous copy out of the pinned scratch has finished
   double* h = (double*)c->h_scratch;
   if (pi) memcpy(h, pi, (size_t)S * 8); else memset(h, 0, (size_t)S * 8);
   if (n_gtr) memcpy(h + S, gtr, n_gtr * 8);
@@ -584,6 +580,7 @@ extern "C" int cb_pmat_build(cb_ctx* c, int model, const double* pi, double beta
   if (x) memcpy(h + S + n_gtr + count, x, (size_t)count * 8);
   memcpy(h + doubles, slots, (size_t)count * 4);
   CU(cudaMemcpyAsync(c->d_scratch, c->h_scratch, bytes, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaEventRecord(c->ev_scratch, c->stream));
   c->h2d += (int64_t)bytes;
   const double* dd = (const double*)c->d_scratch;
   const int threads = (S * S >= 256) ? 256 : ((S * S + 31) / 32 * 32);
@@ -743,27 +740,24 @@ static int snapshot_read_impl(cb_ctx* c, int s, int node, double* out, int32_t* 
 
 // ---------------------------------------------------------------------------- evaluation
 static int ensure_staging(cb_ctx* c, int n_ops, int n_ranges, int n_out) {
-  if (n_ops > c->ops_cap) {
-    int cap = std::max(n_ops, std::max(256, c->ops_cap * 2));
+  const size_t need = (size_t)n_ops * sizeof(OpDesc) + (size_t)n_ranges * sizeof(RangeDesc) + (size_t)c->n_states * 8;
+  if (need > c->stage_cap) {
+    const size_t cap = std::max(need, std::max((size_t)64 << 10, c->stage_cap * 2));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->d_ops) dev_free(c, c->d_ops, (size_t)c->ops_cap * sizeof(OpDesc));
-    if (c->d_images) dev_free(c, c->d_images, (size_t)c->ops_cap * sizeof(S2TImage));
-    if (c->h_ops) cudaFreeHost(c->h_ops);
-    c->d_ops = nullptr; c->h_ops = nullptr; c->d_images = nullptr; c->ops_cap = 0;
-    if (dev_alloc(c, (void**)&c->d_ops, (size_t)cap * sizeof(OpDesc))) return 1;
-    if (c->s2_tiled && dev_alloc(c, (void**)&c->d_images, (size_t)cap * sizeof(S2TImage))) return 1;
-    CU(cudaMallocHost(&c->h_ops, (size_t)cap * sizeof(OpDesc)));
-    c->ops_cap = cap;
+    if (c->d_stage) dev_free(c, c->d_stage, c->stage_cap);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->d_stage = nullptr; c->h_stage = nullptr; c->stage_cap = 0;
+    if (dev_alloc(c, (void**)&c->d_stage, cap)) return 1;
+    CU(cudaMallocHost(&c->h_stage, cap));
+    c->stage_cap = cap;
   }
-  if (n_ranges > c->ranges_cap) {
-    int cap = std::max(n_ranges, std::max(256, c->ranges_cap * 2));
+  if (c->s2_tiled && n_ops > c->images_cap) {
+    const int cap = std::max(n_ops, std::max(256, c->images_cap * 2));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->d_ranges) dev_free(c, c->d_ranges, (size_t)c->ranges_cap * sizeof(RangeDesc));
-    if (c->h_ranges) cudaFreeHost(c->h_ranges);
-    c->d_ranges = nullptr; c->h_ranges = nullptr; c->ranges_cap = 0;
-    if (dev_alloc(c, (void**)&c->d_ranges, (size_t)cap * sizeof(RangeDesc))) return 1;
-    CU(cudaMallocHost(&c->h_ranges, (size_t)cap * sizeof(RangeDesc)));
-    c->ranges_cap = cap;
+    if (c->d_images) dev_free(c, c->d_images, (size_t)c->images_cap * sizeof(S2TImage));
+    c->d_images = nullptr; c->images_cap = 0;
+    if (dev_alloc(c, (void**)&c->d_images, (size_t)cap * sizeof(S2TImage))) return 1;
+    c->images_cap = cap;
   }
   if (n_out > c->out_cap) {
     int cap = std::max(n_out, std::max(1, c->out_cap * 2));
@@ -785,7 +779,7 @@ static int ensure_staging(cb_ctx* c, int n_ops, int n_ranges, int n_out) {
       if (dev_alloc(c, (void**)&c->d_root_dot, (size_t)cap * c->n_cats * c->P * 8)) return 1;
       if (dev_alloc(c, (void**)&c->d_root_exp, (size_t)cap * c->n_cats * c->P * 4)) return 1;
     }
-    CU(cudaMallocHost(&c->h_results, (size_t)cap * 8));
+    CU(cudaHostAlloc(&c->h_results, (size_t)cap * 8, cudaHostAllocMapped));
     c->out_cap = cap;
   }
   return 0;
@@ -793,13 +787,13 @@ static int ensure_staging(cb_ctx* c, int n_ops, int n_ranges, int n_out) {
 
 static LaunchConst make_const(cb_ctx* c) {
   LaunchConst k;
-  k.ops = c->d_ops;
-  k.ranges = c->d_ranges;
+  k.ops = reinterpret_cast<const OpDesc*>(c->d_stage);
+  k.ranges = nullptr;  // set per evaluation: the ranges and pi follow the ops in the staging block
   k.pmats = c->d_pmats;
   k.pmats_lib = c->d_pmats_lib;
   k.staged = c->d_staged;
   k.weights = c->d_weights;
-  k.pi = c->d_pi;
+  k.pi = c->d_pi;   // (overridden per evaluation, see above)
   k.amb = c->d_amb;
   k.block_sums = c->d_block_sums;
   k.tickets = c->d_tickets;
@@ -920,7 +914,7 @@ static int materialize_cherry(cb_ctx* c, int rec, int* buf_out) {
   CU(cudaStreamSynchronize(c->stream));
   int bi;
   if (buffer_acquire(c, &bi)) return 1;
-  OpDesc& op = c->h_ops[0];
+  OpDesc& op = *reinterpret_cast<OpDesc*>(c->h_stage);
   memset(&op, 0, sizeof op);
   op.dst = c->buffers[bi].data;
   op.dst_scale = c->buffers[bi].scale;
@@ -932,10 +926,10 @@ static int materialize_cherry(cb_ctx* c, int rec, int* buf_out) {
     for (int q = 0; q < c->n_cats; ++q) op.pslot[kx][q] = CB_LIB_SLOT | (rec * 2 * c->n_cats + kx * c->n_cats + q);
     op.crec_out[kx] = -1;
   }
-  c->h_ranges[0] = RangeDesc{0, 1, -1, 0};
-  CU(cudaMemcpyAsync(c->d_ops, c->h_ops, sizeof(OpDesc), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_ranges, c->h_ranges, sizeof(RangeDesc), cudaMemcpyHostToDevice, c->stream));
-  const LaunchConst k = make_const(c);
+  *reinterpret_cast<RangeDesc*>(c->h_stage + sizeof(OpDesc)) = RangeDesc{0, 1, -1, 0};
+  CU(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof(OpDesc) + sizeof(RangeDesc), cudaMemcpyHostToDevice, c->stream));
+  LaunchConst k = make_const(c);
+  k.ranges = reinterpret_cast<const RangeDesc*>(c->d_stage + sizeof(OpDesc));
   if (launch_images(c, k, 1)) { buffer_release(c, bi); return 1; }
   if (launch_ranges(c, k, 0, 1, 1, 0)) { buffer_release(c, bi); return 1; }
   CU(cudaStreamSynchronize(c->stream));
@@ -1410,9 +1404,11 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   new_bufs.clear(); new_nodes.clear(); new_cherry_nodes.clear();
   const char* codes = (const char*)c->d_codes;
   const size_t row_bytes = (size_t)c->P * c->code_bytes;
+  OpDesc* const h_ops = reinterpret_cast<OpDesc*>(c->h_stage);
+  const size_t off_ranges = (size_t)total_ops * sizeof(OpDesc), off_pi = off_ranges + (size_t)n_ranges * sizeof(RangeDesc);
   for (int p = 0; p < total_ops; ++p) {
     const PlanOp& po = plan->ops[p];
-    OpDesc& op = c->h_ops[p];
+    OpDesc& op = h_ops[p];
     op.is_root = po.is_root;
     op.pad_ = po.stream;
     op.spill = po.spill;
@@ -1448,8 +1444,8 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
           break;
         case SRC_BUFFER:
           if (pc.ref >= 0) {
-            op.src[kx] = c->h_ops[pc.ref].dst;
-            op.src_scale[kx] = c->h_ops[pc.ref].dst_scale;
+            op.src[kx] = h_ops[pc.ref].dst;
+            op.src_scale[kx] = h_ops[pc.ref].dst_scale;
           } else {
             const Buffer& bf = c->buffers[sin->buf_of_node[~pc.ref]];
             op.src[kx] = bf.data;
@@ -1487,15 +1483,15 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
       }
     }
   }
-  memcpy(c->h_ranges, plan->ranges.data(), (size_t)n_ranges * sizeof(RangeDesc));
+  memcpy(c->h_stage + off_ranges, plan->ranges.data(), (size_t)n_ranges * sizeof(RangeDesc));
+  memcpy(c->h_stage + off_pi, pi, (size_t)c->n_states * 8);
 
   if (ensure_lib_pool(c)) return 1;
-  // upload descriptors + pi, launch
-  CU(cudaMemcpyAsync(c->d_ops, c->h_ops, (size_t)total_ops * sizeof(OpDesc), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_ranges, c->h_ranges, (size_t)n_ranges * sizeof(RangeDesc), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_pi, pi, (size_t)c->n_states * 8, cudaMemcpyHostToDevice, c->stream));
+  // upload descriptors + ranges + pi with one copy, launch
+  const size_t stage_bytes = off_pi + (size_t)c->n_states * 8;
+  CU(cudaMemcpyAsync(c->d_stage, c->h_stage, stage_bytes, cudaMemcpyHostToDevice, c->stream));
   CU(cudaEventRecord(c->ev_stage, c->stream));
-  c->h2d += (int64_t)total_ops * sizeof(OpDesc) + (int64_t)n_ranges * sizeof(RangeDesc) + c->n_states * 8;
+  c->h2d += (int64_t)stage_bytes;
 
   if (c->dmma_rc) {
     // every P matrix the ops use, re-laid out into the shared-memory stage image, in consumption order
@@ -1511,8 +1507,17 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
       c->staged_bytes = cap;
     }
   }
-  const LaunchConst k = make_const(c);
-  CU(cudaEventRecord(c->ev0, c->stream));
+  LaunchConst k = make_const(c);
+  k.ranges = reinterpret_cast<const RangeDesc*>(c->d_stage + off_ranges);
+  k.pi = reinterpret_cast<const double*>(c->d_stage + off_pi);
+  // without a communicator the root kernel writes lnL straight into mapped host memory: no device -> host copy
+  const bool mapped = c->comm == nullptr;
+  if (mapped) {
+    double* dev_view = nullptr;
+    CU(cudaHostGetDevicePointer((void**)&dev_view, c->h_results, 0));
+    k.results = dev_view;
+  }
+  if (c->timing) CU(cudaEventRecord(c->ev0, c->stream));
   if (c->dmma_rc) {
     const unsigned jobs = (unsigned)(total_ops * 2 * C);
     switch ((c->n_states + 7) / 8 * 8) {
@@ -1525,18 +1530,18 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     c->launches += 1;
   }
   if (launch_images(c, k, total_ops)) return 1;
-  CU(cudaEventRecord(c->ev_main0, c->stream));
+  if (c->timing) CU(cudaEventRecord(c->ev_main0, c->stream));
   for (const PlanLaunch& pl : plan->launches)
     if (launch_ranges(c, k, pl.r_begin, pl.r_end, pl.max_ops, pl.n_bufs)) return 1;
-  CU(cudaEventRecord(c->ev_main1, c->stream));
+  if (c->timing) CU(cudaEventRecord(c->ev_main1, c->stream));
   if (!c->family_s2) {
     dim3 grid((unsigned)((c->P + 255) / 256), (unsigned)n_lists);
     root_combine_kernel<<<grid, 256, 0, c->stream>>>(k);
     CU(cudaGetLastError());
     c->launches += 1;
   }
-  CU(cudaEventRecord(c->ev1, c->stream));
-  c->timing_valid = true;
+  if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
+  c->timing_valid = c->timing;
   c->last_bytes_written = plan->bytes_written;
   c->last_bytes_read = plan->bytes_read;
   c->last_counts[0] = total_ops; c->last_counts[1] = plan->n_stored; c->last_counts[2] = plan->n_buffer_reads;
@@ -1547,7 +1552,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     int r = g_nccl.AllReduce(c->d_results, c->d_results, (size_t)n_lists, NCCL_DOUBLE, NCCL_SUM, c->comm, c->stream);
     REQUIRE(r == 0, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
   }
-  CU(cudaMemcpyAsync(c->h_results, c->d_results, (size_t)n_lists * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (!mapped) CU(cudaMemcpyAsync(c->h_results, c->d_results, (size_t)n_lists * 8, cudaMemcpyDeviceToHost, c->stream));
   c->d2h += (int64_t)n_lists * 8;
   c->last_n_out = n_lists;
 
@@ -1628,17 +1633,31 @@ extern "C" int cb_stats(cb_ctx* c, int64_t* launches, int64_t* h2d, int64_t* d2h
   if (dev_bytes) *dev_bytes = c->dev_bytes;
   return 0;
 }
+// cudaMemGetInfo costs 0.5 - 20 ms once tens of GB are allocated, far too much to ask per evaluation: the driver is asked
+// once per device; after that free memory is tracked from the library's own allocations (all contexts of the process).
+static int64_t g_dev_bytes[64] = {0};     // bytes this process holds per device through dev_alloc
+static void dev_account(int device, int64_t delta) { g_dev_bytes[device & 63] += delta; }
+static int64_t g_free_at_query[64], g_held_at_query[64], g_total[64];
+static bool g_queried[64] = {false};
 extern "C" int cb_mem_info(cb_ctx* c, int64_t* free_bytes, int64_t* total_bytes, int64_t* pooled_bytes, int64_t* partial_bytes) {
   REQUIRE(c, "null argument");
-  CU(cudaSetDevice(c->device));
-  size_t fr = 0, tot = 0;
-  CU(cudaMemGetInfo(&fr, &tot));
-  if (c->max_dev_bytes > 0) {  // a capped context sees its cap
-    tot = (size_t)c->max_dev_bytes;
-    fr = (size_t)std::max<int64_t>(0, std::min<int64_t>((int64_t)fr, c->max_dev_bytes - c->dev_bytes));
+  const int d = c->device & 63;
+  if (!g_queried[d]) {
+    CU(cudaSetDevice(c->device));
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    g_free_at_query[d] = (int64_t)fr;
+    g_total[d] = (int64_t)tot;
+    g_held_at_query[d] = g_dev_bytes[d];
+    g_queried[d] = true;
   }
-  if (free_bytes) *free_bytes = (int64_t)fr;
-  if (total_bytes) *total_bytes = (int64_t)tot;
+  int64_t fr = g_free_at_query[d] - (g_dev_bytes[d] - g_held_at_query[d]), tot = g_total[d];
+  if (c->max_dev_bytes > 0) {  // a capped context sees its cap
+    tot = c->max_dev_bytes;
+    fr = std::max<int64_t>(0, std::min<int64_t>(fr, c->max_dev_bytes - c->dev_bytes));
+  }
+  if (free_bytes) *free_bytes = std::max<int64_t>(0, fr);
+  if (total_bytes) *total_bytes = tot;
   if (pooled_bytes) *pooled_bytes = (int64_t)c->free_buffers.size() * (int64_t)c->buffer_bytes;
   if (partial_bytes) *partial_bytes = (int64_t)c->buffer_bytes;
   return 0;
@@ -1735,6 +1754,115 @@ extern "C" int cb_flush_l2(cb_ctx* c) {
 }
 
 
+// --------------------------------------------------------------------------- pattern compression at scale
+// Site-pattern compression (the reference has none, utils.pyx:94-120 keeps every column): unique
+// alignment columns in order of first appearance, with multiplicities.  For alignments of 10^5 .. 10^7 columns the
+// column comparison is done on the GPU: one thread per column folds its n_taxa codes into a 128-bit hash (coalesced
+// reads, HBM-bound), the host groups equal hashes (sort of n_sites 16-byte keys), and a second kernel verifies
+// column by column that every site really equals the representative of its group -- so the result is exact, not
+// probabilistic (a hash collision is reported, the caller then takes the exact host route).
+template <typename T>
+__global__ void __launch_bounds__(256) column_hash_kernel(const T* __restrict__ codes, int n_taxa, int64_t n_sites,
+                                                           unsigned long long* __restrict__ out) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sites) return;
+  unsigned long long h1 = 0xcbf29ce484222325ull, h2 = 0x9e3779b97f4a7c15ull;
+  for (int t = 0; t < n_taxa; ++t) {
+    const unsigned long long v = (unsigned long long)codes[(int64_t)t * n_sites + s] + 1ull;
+    h1 = (h1 ^ v) * 0x100000001b3ull;                                    // FNV-1a
+    h2 = (h2 + v * 0xff51afd7ed558ccdull + (unsigned long long)t) * 0xc4ceb9fe1a85ec53ull;
+    h2 ^= h2 >> 29;
+  }
+  out[2 * s] = h1;
+  out[2 * s + 1] = h2;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) column_verify_kernel(const T* __restrict__ codes, int n_taxa, int64_t n_sites,
+                                                             const int64_t* __restrict__ rep_of_site, unsigned long long* n_bad) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sites) return;
+  const int64_t r = rep_of_site[s];
+  if (r == s) return;
+  bool same = true;
+  for (int t = 0; t < n_taxa && same; ++t) same = codes[(int64_t)t * n_sites + s] == codes[(int64_t)t * n_sites + r];
+  if (!same) atomicAdd(n_bad, 1ull);
+}
+static int compress_impl(int device, const void* codes, int n_taxa, int64_t n_sites, int code_bytes, int64_t* site_to_pattern,
+                         int64_t* first_site, double* weights, int64_t* n_patterns_out) {
+  REQUIRE(codes && site_to_pattern && first_site && weights && n_patterns_out, "null argument");
+  REQUIRE(n_taxa >= 1 && n_sites >= 1 && (code_bytes == 1 || code_bytes == 2), "bad alignment shape");
+  int n_dev = 0;
+  cudaError_t e0 = cudaGetDeviceCount(&n_dev);
+  if (e0 != cudaSuccess || n_dev == 0) return fail("no CUDA device available (%s); cybayes_b200 has no CPU fallback", cudaGetErrorString(e0));
+  REQUIRE(device >= 0 && device < n_dev, "device %d out of range (have %d)", device, n_dev);
+  CU(cudaSetDevice(device));
+  void* d_codes = nullptr;
+  unsigned long long *d_hash = nullptr, *d_bad = nullptr;
+  int64_t* d_rep = nullptr;
+  const size_t code_total = (size_t)n_taxa * n_sites * code_bytes;
+  auto cleanup = [&] { cudaFree(d_codes); cudaFree(d_hash); cudaFree(d_bad); cudaFree(d_rep); };
+#define CUC(call)                                                                                              \
+  do {                                                                                                         \
+    cudaError_t e_ = (call);                                                                                   \
+    if (e_ != cudaSuccess) { cleanup(); return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } \
+  } while (0)
+  CUC(cudaMalloc(&d_codes, code_total));
+  CUC(cudaMalloc(&d_hash, (size_t)n_sites * 16));
+  CUC(cudaMalloc(&d_rep, (size_t)n_sites * 8));
+  CUC(cudaMalloc(&d_bad, 8));
+  CUC(cudaMemcpy(d_codes, codes, code_total, cudaMemcpyHostToDevice));
+  const unsigned blocks = (unsigned)((n_sites + 255) / 256);
+  if (code_bytes == 1) column_hash_kernel<uint8_t><<<blocks, 256>>>((const uint8_t*)d_codes, n_taxa, n_sites, d_hash);
+  else column_hash_kernel<uint16_t><<<blocks, 256>>>((const uint16_t*)d_codes, n_taxa, n_sites, d_hash);
+  CUC(cudaGetLastError());
+  std::vector<unsigned long long> h((size_t)n_sites * 2);
+  CUC(cudaMemcpy(h.data(), d_hash, (size_t)n_sites * 16, cudaMemcpyDeviceToHost));
+  // group equal hashes; the representative of a group is its first site
+  std::vector<int64_t> idx((size_t)n_sites);
+  for (int64_t i = 0; i < n_sites; ++i) idx[i] = i;
+  std::sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) {
+    if (h[2 * a] != h[2 * b]) return h[2 * a] < h[2 * b];
+    if (h[2 * a + 1] != h[2 * b + 1]) return h[2 * a + 1] < h[2 * b + 1];
+    return a < b;
+  });
+  std::vector<int64_t> rep((size_t)n_sites);
+  for (int64_t i = 0; i < n_sites;) {
+    int64_t j = i;
+    while (j < n_sites && h[2 * idx[j]] == h[2 * idx[i]] && h[2 * idx[j] + 1] == h[2 * idx[i] + 1]) rep[idx[j++]] = idx[i];
+    i = j;
+  }
+  CUC(cudaMemcpy(d_rep, rep.data(), (size_t)n_sites * 8, cudaMemcpyHostToDevice));
+  CUC(cudaMemset(d_bad, 0, 8));
+  if (code_bytes == 1) column_verify_kernel<uint8_t><<<blocks, 256>>>((const uint8_t*)d_codes, n_taxa, n_sites, d_rep, d_bad);
+  else column_verify_kernel<uint16_t><<<blocks, 256>>>((const uint16_t*)d_codes, n_taxa, n_sites, d_rep, d_bad);
+  CUC(cudaGetLastError());
+  unsigned long long bad = 0;
+  CUC(cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost));
+#undef CUC
+  cleanup();
+  REQUIRE(bad == 0, "128-bit column hashes collided for %llu sites: use the exact host route", bad);
+  // patterns in order of first appearance (the representative is the smallest site of its group)
+  int64_t n_pat = 0;
+  std::vector<int64_t> pat_of_rep((size_t)n_sites, -1);
+  for (int64_t s = 0; s < n_sites; ++s) {
+    const int64_t r = rep[s];
+    if (r == s) {
+      pat_of_rep[s] = n_pat;
+      first_site[n_pat] = s;
+      weights[n_pat] = 0.0;
+      ++n_pat;
+    }
+    site_to_pattern[s] = pat_of_rep[r];   // r <= s: already numbered
+    weights[pat_of_rep[r]] += 1.0;
+  }
+  *n_patterns_out = n_pat;
+  return 0;
+}
+extern "C" int cb_compress_patterns(int device, const void* codes, int n_taxa, int64_t n_sites, int code_bytes,
+                                    int64_t* site_to_pattern, int64_t* first_site, double* weights, int64_t* n_patterns_out) {
+  return guarded([&] { return compress_impl(device, codes, n_taxa, n_sites, code_bytes, site_to_pattern, first_site, weights, n_patterns_out); });
+}
+
 // ------------------------------------------------------------------------------- native generation loop
 #include "mcmc_native.cuh"
 
@@ -1829,7 +1957,12 @@ extern "C" int cb_chain_run(cb_chain* c, int64_t n_gens, int8_t* move, int8_t* a
                             double* ll_ratio, double* log_u) {
   return guarded([&] {
     REQUIRE(c && n_gens >= 0 && c->ch.snap >= 0, "cb_chain_set_state must come first");
-    return chain_err(c, cbm::run(&c->ch, n_gens, move, accepted, current_ll, proposed_ll, ll_ratio, log_u));
+    cb_ctx* ctx = c->ch.ctx;
+    const bool timing = ctx ? ctx->timing : false;
+    if (ctx) ctx->timing = false;   // no per-evaluation timing events inside the loop
+    const int rc = chain_err(c, cbm::run(&c->ch, n_gens, move, accepted, current_ll, proposed_ll, ll_ratio, log_u));
+    if (ctx) ctx->timing = timing;
+    return rc;
   });
 }
 extern "C" int cb_chain_get_state(cb_chain* c, int32_t* parents, int32_t* children, double* lengths, double* pi, double* rates,

@@ -47,9 +47,14 @@ def load_alignment(input_file, data_type, reader=None):
     return site_dict
 
 
-def move_table(model):
-    """Parameter blocks, their weights and the moves of each block (mat_mcmc_gamma.py:65-84)."""
+def move_table(model, n_rates=None, skip_degenerate_rates=False):
+    """Parameter blocks, their weights and the moves of each block (mat_mcmc_gamma.py:65-84).
+    With skip_degenerate_rates, a GTR model with a single exchangeability (binary data) gets no `rates` block: the
+    reference proposes it anyway and dies in random.sample(range(1), 2) (mcmc_gamma.pyx:189); the default
+    keeps that behaviour so the chain stays comparable with the reference up to its crash."""
     if model == "F81":
+        params, w = ["pi", "tree", "bl", "srates"], [0.5, 3, 4, 0.5]
+    elif model == "GTR" and skip_degenerate_rates and n_rates is not None and n_rates < 2:
         params, w = ["pi", "tree", "bl", "srates"], [0.5, 3, 4, 0.5]
     elif model == "GTR":
         params, w = ["pi", "rates", "tree", "bl", "srates"], [0.5, 0.5, 3, 4, 0.5]
@@ -103,7 +108,7 @@ def spr_tables(tmats, tree_prop, pi, rates, site_rates):
 
 
 def run_chain(input_file, model, n_gen, thin, data_type, output_file, reader=None, seed=1234,
-              out=sys.stdout, fast_spr=False, on_generation=None, diag=None):
+              out=sys.stdout, fast_spr=False, on_generation=None, diag=None, skip_degenerate_rates=False):
     """Run the chain; returns a dict with the final state, counters and timings.  `diag` (a dict) receives, before
     each on_generation call, the acceptance test's two sides: diag["ll_ratio"] and diag["log_u"]."""
     np.random.seed(seed)
@@ -132,7 +137,7 @@ def run_chain(input_file, model, n_gen, thin, data_type, output_file, reader=Non
     print("Initial Likelihood ", state["logLikehood"], file=out)
     initial_lnl = state["logLikehood"]
 
-    params_list, weights, moves_dict, tree_w, bl_w = move_table(model)
+    params_list, weights, moves_dict, tree_w, bl_w = move_table(model, len(state["rates"]), skip_degenerate_rates)
     moves_count, accepts_count = defaultdict(int), defaultdict(int)
     log_fh = open(output_file + ".log", "w")
     trees_fh = open(output_file + ".trees", "w")
@@ -283,9 +288,17 @@ def main(argv=None):
     ap.add_argument("-o", "--output_file", type=str, required=True)
     ap.add_argument("--reader", type=str, default=None, help="override the reader (e.g. readPhy)")
     ap.add_argument("--fast-spr", action="store_true", help="dirty-path scoring of external SPR proposals")
+    ap.add_argument("--native", action="store_true", help="run the generation loop inside the library (same trace)")
+    ap.add_argument("--skip-degenerate-rates", action="store_true",
+                    help="GTR on binary data: do not propose the single exchangeability (the reference crashes there)")
     a = ap.parse_args(argv)
-    res = run_chain(a.input_file, a.model, a.n_gen, a.thin, a.data_type, a.output_file, reader=a.reader,
-                    fast_spr=a.fast_spr)
+    if a.native:
+        from .fastchain import run_chain_native
+        res = run_chain_native(a.input_file, a.model, a.n_gen, a.thin, a.data_type, a.output_file, reader=a.reader,
+                               skip_degenerate_rates=a.skip_degenerate_rates)
+    else:
+        res = run_chain(a.input_file, a.model, a.n_gen, a.thin, a.data_type, a.output_file, reader=a.reader,
+                        fast_spr=a.fast_spr, skip_degenerate_rates=a.skip_degenerate_rates)
     print(f"# {res['gens_per_sec']:.1f} generations/s", file=sys.stderr)
 
 

@@ -104,14 +104,14 @@ def engine_callbacks(engine):
 class NativeChain:
     """Thin object over cb_chain_*; the start state comes from Python, generations run in the library."""
 
-    def __init__(self, engine, state, site_rates, model, binary, use_callbacks=False):
+    def __init__(self, engine, state, site_rates, model, binary, use_callbacks=False, skip_degenerate_rates=False):
         lib = _lib.load()
         self._lib, self.engine = lib, engine
         self.n_taxa, self.n_states, self.n_cats = config.N_TAXA, engine.n_states, engine.n_cats
         tree = state["tree"]
         self.n_edges = len(tree)
         n_rates = len(state["rates"])
-        params, weights, _, tree_w, bl_w = move_table(model)
+        params, weights, _, tree_w, bl_w = move_table(model, n_rates, skip_degenerate_rates)
         cdf = np.ascontiguousarray(np.cumsum(weights) / np.sum(weights))
         tree_cdf = np.ascontiguousarray(np.cumsum(tree_w) / np.sum(tree_w))
         bl_cdf = np.ascontiguousarray(np.cumsum(bl_w) / np.sum(bl_w))
@@ -219,7 +219,7 @@ class NativeChain:
 
 
 def run_chain_native(input_file, model, n_gen, thin, data_type, output_file, reader=None, seed=1234, out=sys.stdout,
-                     on_generation=None, diag=None, use_callbacks=False):
+                     on_generation=None, diag=None, use_callbacks=False, skip_degenerate_rates=False):
     """driver.run_chain with the generation loop in the library; same files, same stdout, same return value."""
     np.random.seed(seed)
     random.seed(seed)
@@ -235,7 +235,8 @@ def run_chain_native(input_file, model, n_gen, thin, data_type, output_file, rea
     site_rates = get_siterates(state["srates"])
     root = state["root"]
     engine, _ = likelihood.engine_for(config.LEAF_LLMAT, config.N_CATS)
-    chain = NativeChain(engine, state, site_rates, model, config.IN_DTYPE == "bin", use_callbacks=use_callbacks)
+    chain = NativeChain(engine, state, site_rates, model, config.IN_DTYPE == "bin", use_callbacks=use_callbacks,
+                        skip_degenerate_rates=skip_degenerate_rates)
     state["logLikehood"] = np.float64(chain.initial_lnl)
     print("Initial Random Tree ", adjlist2newickBL(state["tree"], adjlist2nodes_dict(state["tree"]), root) + ";",
           sep="\t", file=out)

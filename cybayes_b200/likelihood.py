@@ -16,13 +16,16 @@ from operator import itemgetter
 import numpy as np
 
 from . import config, subst
-from .alignment import LeafMatrices, compress_patterns
+from .alignment import LeafMatrices, compress_patterns, compress_patterns_gpu
 from .engine import Engine
 from .subst import PMatTable
 
 # ---------------------------------------------------------------------------- engines
 _engines = {}  # (id(ll_mats), n_cats) -> (ll_mats, Engine, site_to_pattern or None)
+# Pattern compression: alignments of up to COMPRESS_MAX_SITES columns are compressed on the host; longer ones on the GPU
+# unless CYBAYES_COMPRESS_GPU=0.  COMPRESS_MAX_SITES = 0 switches compression off (every column is evaluated, weights 1).
 COMPRESS_MAX_SITES = int(os.environ.get("CYBAYES_COMPRESS_MAX_SITES", "250000"))
+COMPRESS_GPU = os.environ.get("CYBAYES_COMPRESS_GPU", "1") != "0"
 _engine_factory = Engine  # tests substitute a fake engine here
 
 
@@ -65,8 +68,13 @@ def engine_for(ll_mats, n_cats):
     else:
         codes, S, amb = _codes_from_dense(ll_mats, len(ll_mats))
     site_map, weights = None, None
-    if codes.shape[1] <= COMPRESS_MAX_SITES:
-        pat, w, smap = compress_patterns(codes)
+    if 0 < codes.shape[1] <= COMPRESS_MAX_SITES or (COMPRESS_MAX_SITES > 0 and COMPRESS_GPU):
+        # short alignments: NumPy on the host; long ones (where np.unique over 1 KB columns takes minutes): column
+        # hashing + verification on the GPU (same patterns, same order, same weights)
+        if codes.shape[1] <= COMPRESS_MAX_SITES or _engine_factory is not Engine:
+            pat, w, smap = compress_patterns(codes)
+        else:
+            pat, w, smap = compress_patterns_gpu(codes)
         if pat.shape[1] < codes.shape[1]:
             codes, weights, site_map = pat, w, smap
     rank, world = _shard_rank()

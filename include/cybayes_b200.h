@@ -82,6 +82,14 @@ int cb_set_tips(cb_ctx* ctx, int n_taxa, int64_t n_sites, int n_states, int n_ca
                 const void* codes, int code_bytes, const double* amb_sets, int n_amb,
                 const double* weights);
 
+/* Site-pattern compression of a big alignment on the GPU (the reference evaluates every column, utils.pyx:94-120;
+ * summing weight * log-likelihood over unique columns is the same number up to summation order): codes as for
+ * cb_set_tips.  Outputs: site_to_pattern[n_sites], and for the n_patterns unique columns, in order of first
+ * appearance, first_site[] (the column to keep) and weights[] (multiplicities); both sized n_sites by the caller.
+ * Exact: equal 128-bit column hashes are verified column by column on the device; a collision is an error.      */
+int cb_compress_patterns(int device, const void* codes, int n_taxa, int64_t n_sites, int code_bytes,
+                         int64_t* site_to_pattern, int64_t* first_site, double* weights, int64_t* n_patterns_out);
+
 /* ---- transition matrices ---------------------------------------------------------------
  * Device pool of S x S row-major matrices, P[i][j] = Pr(parent i -> child j)
  * (used as P.dot(child) in ML_gamma.pyx:27).  Slot ids are chosen by the caller. */

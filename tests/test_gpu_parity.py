@@ -698,3 +698,52 @@ def test_cache_that_does_not_fit_is_lazy_and_fails_cleanly(gpu_backend, monkeypa
     # the context survives the failure (everything the failed evaluation had acquired went back to the pool)
     l2, c2 = matML(aln.pi, aln.root, leaves, edges, tabs, P, N, 4)
     assert l2 == want and isinstance(c2, LazyPartialCache)
+
+
+@pytest.mark.parametrize("n_taxa,n_sites,n_states", [(64, 300000, 2), (7, 1000, 2), (40, 70000, 23)])
+def test_gpu_pattern_compression_equals_the_host_route(n_taxa, n_sites, n_states, gpu_backend):
+    """cb_compress_patterns (column hashes on the GPU, grouped on the host, verified column by column on the GPU)
+    returns exactly what alignment.compress_patterns returns: same unique columns in order of first appearance, same
+    multiplicities, same site -> pattern map (integer artefacts: bit-exact)."""
+    from cybayes_b200.alignment import compress_patterns, compress_patterns_gpu
+    rng = np.random.default_rng(n_sites)
+    base = rng.integers(0, n_states + 1, size=(n_taxa, max(50, n_sites // 40))).astype(np.uint8)   # many repeated columns
+    codes = np.ascontiguousarray(base[:, rng.integers(0, base.shape[1], size=n_sites)])
+    flip = rng.random(n_sites) < 0.3                                                             # and many singletons
+    codes[rng.integers(0, n_taxa, size=int(flip.sum())), np.nonzero(flip)[0]] ^= 1
+    p0, w0, m0 = compress_patterns(codes)
+    p1, w1, m1 = compress_patterns_gpu(codes)
+    assert p0.shape == p1.shape and np.array_equal(p0, p1)
+    assert np.array_equal(w0, w1) and np.array_equal(m0, m1)
+    assert w1.sum() == n_sites and np.array_equal(p1[:, m1], codes)
+
+
+def test_long_alignment_is_compressed_on_the_gpu(gpu_backend, monkeypatch):
+    """An alignment above the host limit goes through the GPU route inside engine_for; lnL equals the uncompressed
+    evaluation to summation order."""
+    from cybayes_b200 import config
+    from cybayes_b200.alignment import LeafMatrices
+    from cybayes_b200.likelihood import engine_for
+    from cybayes_b200.ML_gamma import matML
+    from cybayes_b200.mcmc_gamma import get_prob_t
+    from cybayes_b200.synthetic import SyntheticAlignment
+    N, P = 32, 40960
+    aln = SyntheticAlignment(N, P, 2, 5, block_sites=2048)
+    codes = aln.codes(0, P)
+    config.N_TAXA, config.N_CHARS, config.N_SITES, config.MODEL, config.IN_DTYPE, config.N_CATS = N, 2, P, "GTR", "bin", 4
+    out = []
+    for limit in (0, 1000):     # 0: no compression; 1000: above the host limit -> GPU route
+        gpu_backend.reset_engines()
+        monkeypatch.setattr(gpu_backend, "COMPRESS_MAX_SITES", limit)
+        leaves = LeafMatrices(codes, 2, np.ones((1, 2)))
+        config.LEAF_LLMAT = leaves
+        tabs = [get_prob_t(aln.pi, aln.tree, aln.er, r) for r in aln.rates]
+        lnl, cache = matML(aln.pi, aln.root, leaves, aln.edge_order(), tabs, P, N, 4)
+        eng, smap = engine_for(leaves, 4)
+        out.append((float(lnl), eng.n_patterns, smap is not None))
+        part = cache.partial(aln.root - 1) if (aln.root - 1) in cache.nodes() else None
+        assert part is None or part.shape == (4, 2, P)      # per-site view, whatever the compression
+        del cache
+    (l0, n0, m0), (l1, n1, m1) = out
+    assert n0 == P and not m0 and n1 < P and m1
+    assert abs(l1 - l0) <= 1e-12 * abs(l0)

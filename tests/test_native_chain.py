@@ -61,3 +61,22 @@ def test_native_chain_reports_the_reference_crash(golden_cases, fake_backend, tm
     case = golden_cases["narrow_GTR"]
     with pytest.raises(CyBayesB200Error, match="Sample larger than population"):
         run_chain_native(golden_io.data_path(case), "GTR", 400, 100, "bin", str(tmp_path / "g"), out=io.StringIO())
+
+
+def test_gtr_on_binary_data_runs_with_the_degenerate_block_skipped(golden_cases, fake_backend, tmp_path):
+    """with skip_degenerate_rates the single exchangeability of a 2-state GTR model is never
+    proposed, so the chain runs -- the Python driver and the native loop agree generation by generation."""
+    from cybayes_b200 import likelihood
+    from cybayes_b200.driver import run_chain
+    from cybayes_b200.fastchain import run_chain_native
+    case = golden_cases["narrow_GTR"]
+    a, b = [], []
+    run_chain(golden_io.data_path(case), "GTR", 120, 40, "bin", str(tmp_path / "p"), out=io.StringIO(), fast_spr=True,
+              skip_degenerate_rates=True, on_generation=lambda i, cur, prop, p, mv, acc, st: a.append((p, mv, acc, float(prop))))
+    likelihood.reset_engines()
+    run_chain_native(golden_io.data_path(case), "GTR", 120, 40, "bin", str(tmp_path / "n"), out=io.StringIO(),
+                     skip_degenerate_rates=True, on_generation=lambda i, cur, prop, p, mv, acc, st: b.append((p, mv, acc, float(prop))))
+    assert len(a) == 120 and not any(p == "rates" for p, _, _, _ in a)
+    assert [x[:3] for x in a] == [x[:3] for x in b]
+    np.testing.assert_allclose([x[3] for x in a], [x[3] for x in b], rtol=1e-12)
+    assert open(str(tmp_path / "p.trees")).read() == open(str(tmp_path / "n.trees")).read()
