@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--config", default="C4", choices=["C4", "C5", "C1", "C2", "C3"])
     ap.add_argument("--taxa", type=int, default=None)
     ap.add_argument("--patterns", type=int, default=None)
-    ap.add_argument("--ref-chunk", type=int, default=10000, help="sites per matML call of --impl reference")
+    ap.add_argument("--ref-chunk", type=int, default=12500, help="sites per matML call of --impl reference (divides 125000)")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / dirty-path / MCMC extras")
     a = ap.parse_args()
     if a.taxa is None:
@@ -125,7 +125,7 @@ def reference_available():
     return os.path.exists(d) and any(f.startswith("ML_gamma") and f.endswith(".so") for f in os.listdir(d))
 
 
-def _ref_setup(taxa, patterns, n_states, seed, chunk):
+def _ref_setup(taxa, patterns, n_states, seed, block):
     """In a worker process: import the compiled, unmodified reference (oracle/_ref/*.so) and describe the alignment."""
     import random
     sys.path.insert(0, os.path.join(REPO, "oracle", "_ref"))
@@ -133,7 +133,7 @@ def _ref_setup(taxa, patterns, n_states, seed, chunk):
     import mcmc_gamma as rmcmc
     import ML_gamma as rml
     from cybayes_b200.synthetic import SyntheticAlignment
-    aln = SyntheticAlignment(taxa, patterns, n_states, seed, block_sites=chunk)
+    aln = SyntheticAlignment(taxa, patterns, n_states, seed, block_sites=block)
     random.seed(1)
     rconfig.N_TAXA, rconfig.N_CHARS = taxa, n_states
     rconfig.MODEL, rconfig.IN_DTYPE = "GTR", ("bin" if n_states == 2 else "multi")
@@ -147,15 +147,27 @@ def _ref_leaves(codes, n_states):
     return {t + 1: np.ascontiguousarray(eye[codes[t]].T) for t in range(codes.shape[0])}
 
 
-def _ref_worker(rank, n_workers, taxa, patterns, n_states, seed, chunk, chunk_ids, n_rounds, barrier, out):
+def _chunk_codes(aln, block, chunk, b, cache):
+    """Columns [b * chunk, (b + 1) * chunk) of the alignment (generated in blocks of `block` columns, exactly as the
+    GPU arm generates them, so both arms evaluate the same data)."""
+    lo = b * chunk
+    blk = lo // block
+    if cache.get("blk") != blk:
+        cache["blk"], cache["codes"] = blk, aln.codes(blk * block, min(aln.n_sites, (blk + 1) * block))
+    off = lo - blk * block
+    return np.ascontiguousarray(cache["codes"][:, off:off + chunk])
+
+
+def _ref_worker(rank, n_workers, taxa, patterns, n_states, seed, block, chunk, chunk_ids, n_rounds, barrier, out):
     """One host core of the reference arm: prepares its chunks of the alignment once, then on every barrier
     evaluates all of them with the reference's ML_gamma.matML (ML_gamma.pyx:7-42)."""
-    aln, rconfig, rml, tmats, pi = _ref_setup(taxa, patterns, n_states, seed, chunk)
+    aln, rconfig, rml, tmats, pi = _ref_setup(taxa, patterns, n_states, seed, block)
     edges = aln.edge_order()
-    mine = []
+    mine, cache = [], {}
     for b in chunk_ids:
-        codes = aln.codes(b * chunk, min(patterns, (b + 1) * chunk))
+        codes = _chunk_codes(aln, block, chunk, b, cache)
         mine.append((_ref_leaves(codes, n_states), codes.shape[1]))
+    cache.clear()
     barrier.wait()                       # everybody is prepared
     for _ in range(n_rounds):
         barrier.wait()                   # start of a step
@@ -183,7 +195,10 @@ def run_reference_arm(a):
     import multiprocessing as mp
     S = 64 if a.config == "C5" else 2
     seed = 20260102 if a.config == "C5" else SEED
+    block = min(a.patterns, 25000 if a.config == "C5" else BLOCK)     # the generation granule of the GPU arm
     chunk = min(a.ref_chunk if a.config != "C5" else 500, a.patterns)
+    if block % chunk:
+        raise SystemExit(f"--ref-chunk must divide {block}")
     n_chunks = -(-a.patterns // chunk)
     cores = min(host_cores(), n_chunks)
     leaf_bytes = a.taxa * S * chunk * 8
@@ -203,13 +218,14 @@ def run_reference_arm(a):
         budget_chunks = min(budget_chunks, cores)
     if budget_chunks < n_chunks:
         ids, sampled = ids[:budget_chunks], True
-    per_worker = [ids[w::cores] for w in range(cores)]
+    per = -(-len(ids) // cores)
+    per_worker = [ids[w * per:(w + 1) * per] for w in range(cores)]     # contiguous: a worker generates 1-2 blocks
     ctx = mp.get_context("spawn")
     barrier = ctx.Barrier(cores + 1)
     out = ctx.Array("d", cores)
     n_rounds = a.warmup + a.steps
-    procs = [ctx.Process(target=_ref_worker, args=(w, cores, a.taxa, a.patterns, S, seed, chunk, per_worker[w], n_rounds,
-                                                   barrier, out)) for w in range(cores)]
+    procs = [ctx.Process(target=_ref_worker, args=(w, cores, a.taxa, a.patterns, S, seed, block, chunk, per_worker[w],
+                                                   n_rounds, barrier, out)) for w in range(cores)]
     for p in procs:
         p.start()
     barrier.wait()
@@ -242,10 +258,10 @@ def run_reference_arm(a):
     }))
 
 
-def _cpu_baseline_child(taxa, patterns, n_states, seed, chunk, block_index, reps, conn):
-    """1 core, spawned so the reference's top-level modules never meet the product's: matML on one chunk."""
-    aln, rconfig, rml, tmats, pi = _ref_setup(taxa, patterns, n_states, seed, chunk)
-    codes = aln.codes(block_index * chunk, min(patterns, (block_index + 1) * chunk))
+def _cpu_baseline_child(taxa, patterns, n_states, seed, block, chunk, reps, conn):
+    """1 core, spawned so the reference's top-level modules never meet the product's: matML on the first chunk."""
+    aln, rconfig, rml, tmats, pi = _ref_setup(taxa, patterns, n_states, seed, block)
+    codes = _chunk_codes(aln, block, chunk, 0, {})
     leaves = _ref_leaves(codes, n_states)
     edges = aln.edge_order()
     rconfig.N_SITES = codes.shape[1]
@@ -261,7 +277,7 @@ def _cpu_baseline_child(taxa, patterns, n_states, seed, chunk, block_index, reps
     conn.close()
 
 
-def cpu_baseline_chunk(a, n_states, seed, chunk, reps=2):
+def cpu_baseline_chunk(a, n_states, seed, block, chunk, reps=2):
     """The compiled reference on ONE core on chunk 0 of the same alignment.  Returns (dict, lnL of the chunk, the
     reference's own P matrices) -- the GPU is then checked on exactly that chunk with exactly those matrices."""
     if not reference_available():
@@ -270,7 +286,7 @@ def cpu_baseline_chunk(a, n_states, seed, chunk, reps=2):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     parent, child = ctx.Pipe()
-    p = ctx.Process(target=_cpu_baseline_child, args=(a.taxa, a.patterns, n_states, seed, chunk, 0, reps, child))
+    p = ctx.Process(target=_cpu_baseline_child, args=(a.taxa, a.patterns, n_states, seed, block, chunk, reps, child))
     p.start()
     secs, lnl, mats = parent.recv()
     p.join()
@@ -524,7 +540,7 @@ def run_c4(a):
         # parity check of BASELINE.md plan step 4: that chunk through the SAME kernel instantiation (>= 75 776
         # patterns) with the reference's own P matrices, single-launch walk and split walk.
         chunk = min(BLOCK, n_local)
-        base, ref_lnl, ref_mats = cpu_baseline_chunk(a, S, SEED, chunk)
+        base, ref_lnl, ref_mats = cpu_baseline_chunk(a, S, SEED, BLOCK, chunk)
         out["cpu_baseline"] = base
         if ref_lnl is not None:
             from cybayes_b200.engine import Engine
@@ -672,7 +688,7 @@ def run_c5(a):
            "data_generation_s": t_gen}
     if rank == 0 and world == 1 and not a.no_extras:
         chunk = min(2000, n_local)
-        base, ref_lnl, ref_mats = cpu_baseline_chunk(a, S, 20260102, chunk, reps=2)
+        base, ref_lnl, ref_mats = cpu_baseline_chunk(a, S, 20260102, block_sites, chunk, reps=2)
         out["cpu_baseline"] = base
         if ref_lnl is not None:
             from cybayes_b200.engine import Engine
