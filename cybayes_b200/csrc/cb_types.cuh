@@ -34,7 +34,7 @@ struct OpDesc {
   int32_t in_buf[2];                       // kind == SRC_STACK: tile buffer holding the child
   int32_t spill;                           // stored AND read back inside the same launch: plain stores
   int32_t pushed;                          // out_buf is a stack slot (the result is popped by a later op)
-  int32_t pad2_[1];
+  int32_t pf_buf;                          // >= 0: child 1 (SRC_STACK, src[1] = its stored partial) is prefetched into this tile buffer
 };
 static_assert(sizeof(OpDesc) == 256, "OpDesc must stay 256 bytes");
 

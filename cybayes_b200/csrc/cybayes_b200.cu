@@ -131,6 +131,7 @@ struct PlanOp {
   int32_t node;
   PlanChild ch[2];
   int32_t out_buf;               // tiled kernel: shared-memory tile buffer of the result, or -1
+  int32_t pf_buf;                // tiled kernel: tile buffer a stored child is prefetched into, or -1
   uint8_t is_root, keep, stream, spill, pushed;
 };
 struct PlanLaunch { int r_begin, r_end, max_ops, n_bufs; };
@@ -167,6 +168,7 @@ struct cb_ctx {
   int s2t_slots = 4;      // its shared-memory stack slots per warp
   int s2t_minb = 2;       // resident blocks per SM it is launched for (2: 128 registers, 4-stage image ring; 3: 85, 3-stage)
   bool s2t_bulk = false;  // stored partials leave through staging tiles + bulk-async copies instead of plain stores
+  bool s2t_prefetch = true;  // stored siblings of a carried child arrive through cp.async two ops ahead (dirty paths)
   S2TImage* d_images = nullptr;  // op images of the current evaluation (s2t_image_kernel)
   int s2_vec = 1;  // sites per thread of the 2-state kernel on large alignments
   int s2_minb = 3; // its __launch_bounds__ min blocks per SM (experiment knob)
@@ -296,6 +298,7 @@ static int create_impl(int device, cb_ctx** out) {
   if (getenv("CYBAYES_S2_NO_CS")) c->s2_stream_stores = false;
   if (const char* v = getenv("CYBAYES_S2T_MINB")) c->s2t_minb = atoi(v) == 3 ? 3 : 2;
   if (getenv("CYBAYES_S2T_BULK")) c->s2t_bulk = atoi(getenv("CYBAYES_S2T_BULK")) != 0;
+  if (getenv("CYBAYES_S2T_PREFETCH")) c->s2t_prefetch = atoi(getenv("CYBAYES_S2T_PREFETCH")) != 0;
   c->s2t_slots = c->s2t_minb == 3 ? 3 : 4;
   if (const char* v = getenv("CYBAYES_S2T_SLOTS")) c->s2t_slots = std::max(0, std::min(8, atoi(v)));
   if (getenv("CYBAYES_NO_PLAN_CACHE")) c->no_plan_cache = true;
@@ -918,7 +921,7 @@ static int materialize_cherry(cb_ctx* c, int rec, int* buf_out) {
   memset(&op, 0, sizeof op);
   op.dst = c->buffers[bi].data;
   op.dst_scale = c->buffers[bi].scale;
-  op.out_buf = -1;
+  op.out_buf = op.pf_buf = -1;
   op.pushed = 0;
   for (int kx = 0; kx < 2; ++kx) {
     op.kind[kx] = SRC_TIP;
@@ -1190,7 +1193,7 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
       po.is_root = (j == n - 1);
       REQUIRE(!po.is_root || p == n - 1, "internal error: root is not last");
       po.keep = po.stream = po.spill = po.pushed = 0;
-      po.out_buf = -1;
+      po.out_buf = po.pf_buf = -1;
       for (int kx = 0; kx < 2; ++kx) {
         PlanChild& pc = po.ch[kx];
         const int ch = L[j].child[kx];
@@ -1253,15 +1256,32 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
         else if (c->s2t_bulk && po.keep && !po.spill) { po.out_buf = staging_rr; staging_rr ^= 1; }
       }
     }
+    if (c->s2_tiled && c->s2t_prefetch) {
+      // A stored partial that comes from the input snapshot or from an earlier launch and is read beside a carried child
+      // is prefetched into a tile buffer two ops ahead (three rotating buffers above the stack slots) and then read like
+      // a stack slot: a dirty path keeps three sibling tiles per warp in flight instead of exposing one DRAM latency per op.
+      const int pf_base = slot_base + K;
+      int rr = 0;
+      for (int p = 0; p < n; ++p) {
+        PlanOp& po = plan.ops[base + p];
+        if (po.ch[0].kind != SRC_CARRIED || po.ch[1].kind != SRC_BUFFER) continue;
+        const int ref = po.ch[1].ref;
+        const bool other_launch = ref < 0 || !same_range(ref - base, p);
+        if (!other_launch) continue;
+        po.ch[1].kind = SRC_STACK;     // read from the tile buffer; po.ch[1].ref keeps naming the stored partial
+        po.pf_buf = pf_base + rr;
+        rr = (rr + 1) % 3;
+      }
+    }
 
     // ranges and launches
     auto bufs_of = [&](int p0, int p1) {
       int nb = 0;
       for (int p = p0; p < p1; ++p) {
         const PlanOp& po = plan.ops[base + p];
-        nb = std::max(nb, po.out_buf + 1);
+        nb = std::max(nb, std::max(po.out_buf, po.pf_buf) + 1);
         for (int kx = 0; kx < 2; ++kx)
-          if (po.ch[kx].kind == SRC_STACK) nb = std::max(nb, po.ch[kx].ref + 1);
+          if (po.ch[kx].kind == SRC_STACK && po.pf_buf < 0) nb = std::max(nb, po.ch[kx].ref + 1);
       }
       return nb;
     };
@@ -1311,9 +1331,9 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
     int mx = 0, nb = 0;
     for (const RangeDesc& r : plan.ranges) mx = std::max(mx, r.end - r.begin);
     for (const PlanOp& po : plan.ops) {
-      nb = std::max(nb, po.out_buf + 1);
+      nb = std::max(nb, std::max(po.out_buf, po.pf_buf) + 1);
       for (int kx = 0; kx < 2; ++kx)
-        if (po.ch[kx].kind == SRC_STACK) nb = std::max(nb, po.ch[kx].ref + 1);
+        if (po.ch[kx].kind == SRC_STACK && po.pf_buf < 0) nb = std::max(nb, po.ch[kx].ref + 1);
     }
     plan.launches.push_back({0, (int)plan.ranges.size(), mx, nb});
   }
@@ -1413,6 +1433,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     op.pad_ = po.stream;
     op.spill = po.spill;
     op.pushed = po.pushed;
+    op.pf_buf = po.pf_buf;
     op.out_buf = po.out_buf;
     op.dst = nullptr;
     op.dst_scale = nullptr;
@@ -1453,7 +1474,12 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
           }
           break;
         case SRC_STACK:
-          op.in_buf[kx] = pc.ref;
+          if (po.pf_buf >= 0 && kx == 1) {   // a prefetched stored partial: the source is a buffer, the op reads the tile buffer
+            op.in_buf[kx] = po.pf_buf;
+            op.src[kx] = pc.ref >= 0 ? (const void*)h_ops[pc.ref].dst : (const void*)c->buffers[sin->buf_of_node[~pc.ref]].data;
+          } else {
+            op.in_buf[kx] = pc.ref;
+          }
           break;
         case SRC_CHERRY:
           if (pc.ref >= 0) {  // folded out of the caller's list: its P matrices are the caller's slots

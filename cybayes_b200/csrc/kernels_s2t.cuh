@@ -53,7 +53,8 @@ struct S2TImage {
   int32_t out_buf;           // shared-memory tile buffer that receives the result (-1: registers only)
   int32_t in_buf[2];         // SRC_STACK: tile buffer holding the child
   int32_t store_mode;        // S2TStore
-  int32_t pad_[2];
+  int32_t pf_buf;            // >= 0: child 1 is a stored partial that is PREFETCHED into this tile buffer two ops ahead
+  int32_t pad_;              //       (cp.async, no destination registers) and then read like a stack slot
 };
 static_assert(sizeof(S2TImage) == 1408, "S2TImage must stay 1408 bytes (a multiple of 16)");
 
@@ -133,6 +134,9 @@ __device__ __forceinline__ void s2t_cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s2t_smem_addr(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void s2t_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void s2t_cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s2t_smem_addr(smem)), "l"(gmem) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void s2t_cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
@@ -171,7 +175,8 @@ __global__ void __launch_bounds__(32) s2t_image_kernel(const LaunchConst k, int 
       else mode |= S2T_ST_GLOBAL | (op->pad_ ? S2T_ST_STREAM : 0);
     }
     im->store_mode = mode;
-    im->pad_[0] = im->pad_[1] = 0;
+    im->pf_buf = op->pf_buf;
+    im->pad_ = 0;
   }
   // P matrices of internal and tip children (one thread per child, category and row)
   for (int idx = t; idx < 4 * C; idx += 32) {
@@ -359,6 +364,19 @@ __global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const Laun
     const S2TImage& im = ring[o % RING];
     s2t_cp_async4(mycodes + (o % S2T_CODE_SLOTS) * (4 * S2T_W) + 4 * lane, static_cast<const char*>(im.rows[lane >> 3]) + code_off);
   };
+  // a stored partial that op o reads as its second child: the warp's tile (TB bytes, contiguous) in 16-byte pieces
+  auto issue_prefetch = [&](int o) {
+    const S2TImage& im = ring[o % RING];
+    if (im.pf_buf >= 0) {
+      const char* src = im.src[1] + tile_off;
+      unsigned char* dst = mybufs + (size_t)im.pf_buf * TB;
+#pragma unroll
+      for (int j = 0; j < (TB / 16 + 31) / 32; ++j) {
+        const int idx = lane + 32 * j;
+        if (idx < TB / 16) s2t_cp_async16(dst + 16 * idx, src + 16 * idx);
+      }
+    }
+  };
   auto wait_chunk_of = [&](int o) {  // the image of op o is in the ring (o is the first op of its chunk)
     const int c1 = o / S2T_RING_OPS;
     s2t_mbar_wait(&full_bar[c1 % S2T_RING_STAGES], (unsigned)(c1 / S2T_RING_STAGES) & 1u);
@@ -386,10 +404,12 @@ __global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const Laun
     // code pipeline: the copies of op o + 2 are issued at the end of op o; one commit group per op
     wait_chunk_of(0);
     issue_codes(0);
+    issue_prefetch(0);
     s2t_cp_async_commit();
     if (nops > 1) {
       if (S2T_RING_OPS == 1) wait_chunk_of(1);
       issue_codes(1);
+      issue_prefetch(1);
     }
     s2t_cp_async_commit();
 
@@ -513,6 +533,7 @@ __global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const Laun
           }
         }
         issue_codes(o + 2);
+        issue_prefetch(o + 2);
       }
       s2t_cp_async_commit();
 
