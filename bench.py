@@ -384,6 +384,7 @@ def run_c4(a):
     clocks = ClockSampler(local) if rank == 0 else None
     st0 = eng.stats()
     kernel_ms, main_ms = [], []
+    eng.host_profile()
     eng.mark(0)
     t0 = time.perf_counter()
     for _ in range(a.steps):
@@ -393,6 +394,7 @@ def run_c4(a):
     eng.mark(1)
     eng.sync()
     wall = time.perf_counter() - t0
+    host_prof = eng.host_profile()
     dev_ms = eng.mark_elapsed_ms()
     st1 = eng.stats()
     info = eng.last_eval_info()
@@ -486,6 +488,7 @@ def run_c4(a):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config_dict(a),
         "lnL": lnl, "wall_ms_per_step": wall_ms / a.steps, "host_ms_per_step": ms_per_step - statistics.mean(kernel_ms),
+        "host_us_per_eval_rank0": host_prof,
         "roofline": roofline, "e2e": e2e,
         "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"], "clocks": clock_rec,
         "data_generation_s": t_gen,

@@ -71,6 +71,7 @@ SIGNATURES = {
     "cb_last_eval_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cb_last_eval_main_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cb_last_eval_info": (C.c_int, [C.c_void_p, c_i64p, c_i64p, c_i32p]),
+    "cb_host_profile": (C.c_int, [C.c_void_p, c_f64p, C.c_int]),
     "cb_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "cb_mark_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cb_sync": (C.c_int, [C.c_void_p]),

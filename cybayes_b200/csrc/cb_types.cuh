@@ -65,7 +65,19 @@ struct LaunchConst {
   int32_t n_amb;          // rows of `amb`
   const void* codes;      // tip state codes [n_taxa][n_sites]
   int32_t s2t_bulk;       // tiled 2-state kernel: stored partials leave through shared memory + bulk-async copies
-  int32_t pad_;
+  // Site-sharded multi-GPU: the scalar all-reduce fused into the root kernel over NVLink peer memory (kernels_s2.cuh,
+  // block_reduce_to_result).  n_ranks <= 1: single GPU.
+  int32_t n_ranks, my_rank;
+  unsigned long long epoch;            // evaluation counter, identical on every rank
+  struct Mail* mailbox;                // this rank's mailbox [2][CB_MB_OUTS][n_ranks]
+  struct Mail* const* peer_mailbox;    // device array: every rank's mailbox (peer pointers opened through CUDA IPC)
+  int32_t* comm_error;                 // set when a peer never delivered (timeout)
+};
+
+constexpr int CB_MB_OUTS = 64;          // results per evaluation the fused all-reduce handles (larger batches use NCCL)
+struct Mail {
+  double v;
+  unsigned long long e;
 };
 
 }  // namespace cb

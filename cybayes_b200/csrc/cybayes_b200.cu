@@ -14,6 +14,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <time.h>
+
 #include <algorithm>
 #include <exception>
 #include <new>
@@ -52,6 +54,12 @@ static int fail(const char* fmt, ...) {
   } while (0)
 
 
+static inline double now_us() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
 // No C++ exception may cross the C ABI: every entry point that allocates runs under this guard.
 template <typename F>
 static int guarded(F&& f) {
@@ -74,6 +82,7 @@ struct NcclApi {
   int (*GetUniqueId)(NcclId*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, NcclId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -89,13 +98,14 @@ static int load_nccl() {
   g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(g_nccl.lib, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, NcclId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
   g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
   REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy,
           "libnccl is missing expected symbols");
   return 0;
 }
-enum { NCCL_DOUBLE = 8, NCCL_SUM = 0 };  // ncclFloat64 / ncclSum in nccl.h
+enum { NCCL_DOUBLE = 8, NCCL_SUM = 0, NCCL_INT8 = 0 };  // ncclFloat64 / ncclSum / ncclInt8 in nccl.h
 
 // ------------------------------------------------------------------------------ context
 constexpr int DMMA_RC_MIN_STATES = 9;   // measured: 1.65x (S = 23, 2304 patterns) .. 3.1x (S = 30, 16384) over the plain FP64 kernel
@@ -214,9 +224,15 @@ struct cb_ctx {
   // L2 flush
   void* d_flush = nullptr;
   size_t flush_bytes = 0;
-  // NCCL
+  // NCCL (set-up, and the all-reduce of batches with more than CB_MB_OUTS results) + the fused all-reduce's mailboxes
   ncclComm_t comm = nullptr;
-  int n_ranks = 1;
+  int n_ranks = 1, rank = 0;
+  bool fused_allreduce = false;
+  Mail* d_mailbox = nullptr;           // [2][CB_MB_OUTS][n_ranks], written by the peers
+  Mail** d_peer_mailbox = nullptr;     // device array of every rank's mailbox
+  std::vector<void*> peer_opened;      // IPC mappings to close
+  int32_t* d_comm_error = nullptr;
+  unsigned long long epoch = 0;
   // plans of full evaluations, cached per topology; scratch plan of dirty-path evaluations
   std::vector<EvalPlan> plans;
   EvalPlan scratch_plan;
@@ -224,6 +240,7 @@ struct cb_ctx {
   bool no_plan_cache = false;
   std::vector<int> work_new_bufs, work_new_nodes, work_cherry_nodes;
   cudaEvent_t ev_main0 = nullptr, ev_main1 = nullptr;  // around the pruning launches proper (without pre-passes)
+  double host_us[6] = {0, 0, 0, 0, 0, 0};  // accumulated per-evaluation host time: plan, fill, upload+launch, sync, bookkeeping, calls
   int64_t last_bytes_written = 0, last_bytes_read = 0;
   int32_t last_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // stats
@@ -363,6 +380,10 @@ extern "C" int cb_destroy(cb_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (void* ptr : c->peer_opened) cudaIpcCloseMemHandle(ptr);
+  if (c->d_mailbox) cudaFree(c->d_mailbox);
+  if (c->d_peer_mailbox) cudaFree(c->d_peer_mailbox);
+  if (c->d_comm_error) cudaFree(c->d_comm_error);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   free_alignment(c);
   if (c->d_stage) dev_free(c, c->d_stage, c->stage_cap);
@@ -403,6 +424,49 @@ extern "C" int cb_comm_init(cb_ctx* c, const void* id128, int rank, int n_ranks)
   int r = g_nccl.CommInitRank(&c->comm, n_ranks, id, rank);
   REQUIRE(r == 0, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
   c->n_ranks = n_ranks;
+  c->rank = rank;
+  // Fused scalar all-reduce over NVLink peer memory: every rank owns a mailbox, opens the others' through CUDA IPC
+  // (handles exchanged once with ncclAllGather) and from then on the root kernel delivers and collects the shard sums
+  // itself.  Any failure here just leaves the NCCL all-reduce in place.
+  if (n_ranks > 1 && n_ranks <= 32 && g_nccl.AllGather && !getenv("CYBAYES_NO_FUSED_ALLREDUCE")) {
+    const size_t mb_bytes = (size_t)2 * CB_MB_OUTS * n_ranks * sizeof(Mail);
+    cudaIpcMemHandle_t* d_handles = nullptr;
+    std::vector<cudaIpcMemHandle_t> handles(n_ranks);
+    bool ok = cudaMalloc((void**)&c->d_mailbox, mb_bytes) == cudaSuccess && cudaMemset(c->d_mailbox, 0, mb_bytes) == cudaSuccess &&
+              cudaMalloc((void**)&d_handles, sizeof(cudaIpcMemHandle_t) * n_ranks) == cudaSuccess &&
+              cudaMalloc((void**)&c->d_peer_mailbox, sizeof(Mail*) * n_ranks) == cudaSuccess &&
+              cudaMalloc((void**)&c->d_comm_error, 4) == cudaSuccess && cudaMemset(c->d_comm_error, 0, 4) == cudaSuccess;
+    if (ok) ok = cudaIpcGetMemHandle(&handles[rank], c->d_mailbox) == cudaSuccess &&
+                 cudaMemcpy(d_handles + rank, &handles[rank], sizeof(cudaIpcMemHandle_t), cudaMemcpyHostToDevice) == cudaSuccess;
+    // every rank must take part in the collective, whatever happened locally
+    const int gr = g_nccl.AllGather(ok ? (const void*)(d_handles + rank) : (const void*)d_handles, d_handles, sizeof(cudaIpcMemHandle_t),
+                                    NCCL_INT8, c->comm, c->stream);
+    ok = ok && gr == 0 && cudaStreamSynchronize(c->stream) == cudaSuccess &&
+         cudaMemcpy(handles.data(), d_handles, sizeof(cudaIpcMemHandle_t) * n_ranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+    std::vector<Mail*> peers(n_ranks, nullptr);
+    for (int q = 0; ok && q < n_ranks; ++q) {
+      if (q == rank) { peers[q] = c->d_mailbox; continue; }
+      void* ptr = nullptr;
+      ok = cudaIpcOpenMemHandle(&ptr, handles[q], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      if (ok) { peers[q] = (Mail*)ptr; c->peer_opened.push_back(ptr); }
+    }
+    if (ok) ok = cudaMemcpy(c->d_peer_mailbox, peers.data(), sizeof(Mail*) * n_ranks, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (d_handles) cudaFree(d_handles);
+    // all ranks agree on the outcome (one rank without peer access must not leave the others waiting in a kernel)
+    double* d_flag = nullptr;
+    double flag = ok ? 0.0 : 1.0;
+    if (cudaMalloc((void**)&d_flag, 8) == cudaSuccess) {
+      cudaMemcpy(d_flag, &flag, 8, cudaMemcpyHostToDevice);
+      g_nccl.AllReduce(d_flag, d_flag, 1, NCCL_DOUBLE, NCCL_SUM, c->comm, c->stream);
+      cudaStreamSynchronize(c->stream);
+      cudaMemcpy(&flag, d_flag, 8, cudaMemcpyDeviceToHost);
+      cudaFree(d_flag);
+    } else {
+      flag = 1.0;
+    }
+    cudaGetLastError();
+    c->fused_allreduce = (flag == 0.0);
+  }
   return 0;
 }
 
@@ -813,7 +877,12 @@ static LaunchConst make_const(cb_ctx* c) {
   k.n_amb = c->n_amb;
   k.codes = c->d_codes;
   k.s2t_bulk = c->s2t_bulk ? 1 : 0;
-  k.pad_ = 0;
+  k.n_ranks = 1;
+  k.my_rank = 0;
+  k.epoch = 0;
+  k.mailbox = nullptr;
+  k.peer_mailbox = nullptr;
+  k.comm_error = nullptr;
   return k;
 }
 
@@ -1256,11 +1325,14 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
         else if (c->s2t_bulk && po.keep && !po.spill) { po.out_buf = staging_rr; staging_rr ^= 1; }
       }
     }
-    if (c->s2_tiled && c->s2t_prefetch) {
-      // A stored partial that comes from the input snapshot or from an earlier launch and is read beside a carried child
-      // is prefetched into a tile buffer two ops ahead (three rotating buffers above the stack slots) and then read like
-      // a stack slot: a dirty path keeps three sibling tiles per warp in flight instead of exposing one DRAM latency per op.
-      const int pf_base = slot_base + K;
+    bool uses_stack = false;
+    for (int j = 0; j < n; ++j) uses_stack = uses_stack || push_slot[j] >= 0;
+    if (c->s2_tiled && c->s2t_prefetch && !uses_stack && !c->s2t_bulk) {
+      // Dirty paths and other lists that need no stack: a stored partial that comes from the input snapshot (or an earlier
+      // launch) and is read beside a carried child is prefetched into a tile buffer two ops ahead (three rotating
+      // buffers) and then read like a stack slot: the path keeps three sibling tiles per warp in flight instead of
+      // exposing one DRAM latency per op.
+      const int pf_base = 0;
       int rr = 0;
       for (int p = 0; p < n; ++p) {
         PlanOp& po = plan.ops[base + p];
@@ -1366,6 +1438,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   REQUIRE(!(want_snap && n_lists != 1), "snapshots are only kept for single evaluations");
   CU(cudaSetDevice(c->device));
 
+  const double t_begin = now_us();
   // ---- the plan: cached per (op list, flags) for full evaluations, built on the spot for dirty paths
   const int split_env = getenv("CYBAYES_WALK_SPLIT") ? atoi(getenv("CYBAYES_WALK_SPLIT")) : 0;
   EvalPlan* plan = nullptr;
@@ -1414,6 +1487,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
 
   if (ensure_staging(c, total_ops, n_ranges, n_lists)) return 1;
   CU(cudaEventSynchronize(c->ev_stage));  // previous H2D of the staging area finished
+  const double t_planned = now_us();
 
   // ---- fill the descriptors: buffers, pointers, P slots
   const Snapshot* sin = snapshot_in >= 0 ? &c->snaps[snapshot_in] : nullptr;
@@ -1512,6 +1586,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   memcpy(c->h_stage + off_ranges, plan->ranges.data(), (size_t)n_ranges * sizeof(RangeDesc));
   memcpy(c->h_stage + off_pi, pi, (size_t)c->n_states * 8);
 
+  const double t_filled = now_us();
   if (ensure_lib_pool(c)) return 1;
   // upload descriptors + ranges + pi with one copy, launch
   const size_t stage_bytes = off_pi + (size_t)c->n_states * 8;
@@ -1536,8 +1611,19 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   LaunchConst k = make_const(c);
   k.ranges = reinterpret_cast<const RangeDesc*>(c->d_stage + off_ranges);
   k.pi = reinterpret_cast<const double*>(c->d_stage + off_pi);
-  // without a communicator the root kernel writes lnL straight into mapped host memory: no device -> host copy
-  const bool mapped = c->comm == nullptr;
+  // Sharded over GPUs: the root kernel all-reduces the shard sums itself over peer memory (batches beyond CB_MB_OUTS
+  // results: ncclAllReduce).  Either way without NCCL in the step the kernel writes lnL straight into mapped host
+  // memory: no device -> host copy.
+  const bool fused = c->comm != nullptr && c->fused_allreduce && n_lists <= CB_MB_OUTS;
+  if (fused) {
+    k.n_ranks = c->n_ranks;
+    k.my_rank = c->rank;
+    k.epoch = ++c->epoch;
+    k.mailbox = c->d_mailbox;
+    k.peer_mailbox = c->d_peer_mailbox;
+    k.comm_error = c->d_comm_error;
+  }
+  const bool mapped = c->comm == nullptr || fused;
   if (mapped) {
     double* dev_view = nullptr;
     CU(cudaHostGetDevicePointer((void**)&dev_view, c->h_results, 0));
@@ -1574,7 +1660,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   c->last_counts[3] = plan->n_stack; c->last_counts[4] = plan->n_spills; c->last_counts[5] = plan->n_cherries;
   c->last_counts[6] = (int)plan->launches.size(); c->last_counts[7] = (int)c->plan_builds;
 
-  if (c->comm) {
+  if (c->comm && !fused) {
     int r = g_nccl.AllReduce(c->d_results, c->d_results, (size_t)n_lists, NCCL_DOUBLE, NCCL_SUM, c->comm, c->stream);
     REQUIRE(r == 0, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
   }
@@ -1582,6 +1668,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   c->d2h += (int64_t)n_lists * 8;
   c->last_n_out = n_lists;
 
+  const double t_launched = now_us();
   // bookkeeping (stream-ordered: temporaries may be recycled by later launches on this stream)
   guard.armed = false;
   if (want_snap) {
@@ -1623,8 +1710,20 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     if (snapshot_out) *snapshot_out = -1;
   }
 
+  const double t_booked = now_us();
+  c->host_us[0] += t_planned - t_begin;
+  c->host_us[1] += t_filled - t_planned;
+  c->host_us[2] += t_launched - t_filled;
+  c->host_us[4] += t_booked - t_launched;
+  c->host_us[5] += 1.0;
   if (!(flags & CB_EVAL_NO_SYNC)) {
     CU(cudaStreamSynchronize(c->stream));
+    c->host_us[3] += now_us() - t_booked;
+    if (fused && c->h_results[0] != c->h_results[0]) {  // NaN: did a peer fail to deliver its shard sum?
+      int32_t err = 0;
+      CU(cudaMemcpy(&err, c->d_comm_error, 4, cudaMemcpyDeviceToHost));
+      REQUIRE(err == 0, "fused all-reduce: a peer GPU never delivered its shard sum (rank %d of %d waited 10 s)", c->rank, c->n_ranks);
+    }
     if (lnl_out) memcpy(lnl_out, c->h_results, (size_t)n_lists * 8);
   }
   return 0;
@@ -1700,6 +1799,12 @@ extern "C" int cb_last_eval_main_ms(cb_ctx* c, float* ms) {
   CU(cudaSetDevice(c->device));
   CU(cudaEventSynchronize(c->ev_main1));
   CU(cudaEventElapsedTime(ms, c->ev_main0, c->ev_main1));
+  return 0;
+}
+extern "C" int cb_host_profile(cb_ctx* c, double* us6, int reset) {
+  REQUIRE(c && us6, "null argument");
+  memcpy(us6, c->host_us, sizeof c->host_us);
+  if (reset) memset(c->host_us, 0, sizeof c->host_us);
   return 0;
 }
 extern "C" int cb_last_eval_info(cb_ctx* c, int64_t* bytes_written, int64_t* bytes_read, int32_t* counts8) {

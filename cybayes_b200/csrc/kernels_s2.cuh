@@ -47,6 +47,36 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Scalar all-reduce over the GPUs of a site-sharded evaluation, fused into the kernel that produces the shard's sum
+// (one warp of its last block): lane r stores (sum, epoch) into rank r's mailbox through NVLink peer memory, then waits
+// for rank r's entry in the local mailbox; the total is added in rank order, so every rank gets the same bits.  Mailboxes
+// are double-buffered by epoch parity: a rank can be at most one evaluation ahead of the slowest one (to finish
+// evaluation e it needs everybody's entry of e).  Replaces a separate ncclAllReduce launch + device -> host copy.
+__device__ __forceinline__ double fused_allreduce(double s, const LaunchConst& k, int out_index, int lane) {
+  s = __shfl_sync(0xffffffffu, s, 0);
+  const int n = k.n_ranks;
+  const size_t slot = ((size_t)(k.epoch & 1ull) * CB_MB_OUTS + out_index) * n;
+  double v = 0.0;
+  if (lane < n) {
+    Mail* dst = k.peer_mailbox[lane] + slot + k.my_rank;
+    *reinterpret_cast<volatile double*>(&dst->v) = s;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&dst->e) = k.epoch;
+    const Mail* src = k.mailbox + slot + lane;
+    const long long t0 = clock64();
+    bool ok = true;
+    while (*reinterpret_cast<const volatile unsigned long long*>(&src->e) != k.epoch) {
+      if (clock64() - t0 > 20000000000ll) { ok = false; break; }   // ~10 s: a peer died; report instead of hanging
+    }
+    __threadfence_system();
+    v = *reinterpret_cast<const volatile double*>(&src->v);
+    if (!ok) { *k.comm_error = 1; v = __longlong_as_double(0x7ff8000000000000ll); }
+  }
+  double total = 0.0;
+  for (int r = 0; r < n; ++r) total += __shfl_sync(0xffffffffu, v, r);   // rank order: identical bits on every rank
+  return total;
+}
+
 // Deterministic block -> grid reduction of one double per thread.
 // red must hold 32 doubles; every thread of the block must call this.
 __device__ __forceinline__ void block_reduce_to_result(double v, const LaunchConst& k, int out_index,
@@ -72,6 +102,7 @@ __device__ __forceinline__ void block_reduce_to_result(double v, const LaunchCon
     double s = 0.0;
     for (unsigned i = lane; i < gridDim.x; i += 32) s += __ldcg(bs + i);
     s = warp_sum(s);
+    if (k.n_ranks > 1) s = fused_allreduce(s, k, out_index, lane);
     if (lane == 0) {
       k.results[out_index] = s;
       k.tickets[out_index] = 0u;

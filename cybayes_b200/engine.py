@@ -246,6 +246,14 @@ class Engine(SlotPool):
         out["bytes_written"], out["bytes_read"] = w.value, r.value
         return out
 
+    def host_profile(self, reset=True):
+        """Mean host microseconds per evaluation call since the last reset, by phase."""
+        a = np.zeros(6)
+        check(self._lib.cb_host_profile(self._ctx, _f64(a), 1 if reset else 0))
+        n = max(a[5], 1.0)
+        return {"plan": a[0] / n, "fill": a[1] / n, "upload_launch": a[2] / n, "wait": a[3] / n, "bookkeeping": a[4] / n,
+                "calls": int(a[5])}
+
     def mark(self, which):
         check(self._lib.cb_mark(self._ctx, int(which)))
 

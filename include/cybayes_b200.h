@@ -193,6 +193,9 @@ int cb_last_eval_main_ms(cb_ctx* ctx, float* ms_out);
  * counts8 = { ops run, partials stored, partials read back, children popped from the shared-memory stack,
  * partials stored and re-read inside one launch, cherries folded, pruning launches, plans built so far }. */
 int cb_last_eval_info(cb_ctx* ctx, int64_t* bytes_written, int64_t* bytes_read, int32_t* counts8);
+/* host microseconds cb_eval / cb_eval_batch have spent since the last reset, by phase: us6 = { plan look-up or build,
+ * descriptor fill, upload + launches, wait for the result, snapshot bookkeeping, number of calls } */
+int cb_host_profile(cb_ctx* ctx, double* us6, int reset);
 /* CUDA events on the engine's stream: cb_mark(ctx, 0) ... work ... cb_mark(ctx, 1); elapsed = device ms */
 int cb_mark(cb_ctx* ctx, int which);
 int cb_mark_elapsed_ms(cb_ctx* ctx, float* ms_out);
