@@ -428,7 +428,7 @@ def run_c4(a):
                 "eval_ms_incl_prepass": statistics.mean(kernel_ms), "peak_source": peak_src,
                 "launches_per_eval": (st1["kernel_launches"] - st0["kernel_launches"]) / a.steps,
                 "op_list": {k: info[k] for k in ("ops", "stored", "read_back", "stack_pops", "spills", "cherries_folded",
-                                                 "launches")},
+                                                 "small_records", "launches")},
                 "survey_8d": {"algorithmic_bytes_per_eval": alg_bytes, "GBps": alg_bytes / (k_ms * 1e-3) / 1e9,
                               "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak,
                               "note": "SURVEY 8(d) counts every non-root partial as written and read back; the walk "

@@ -32,8 +32,9 @@ struct OpDesc {
   // tiled 2-state kernel (kernels_s2t.cuh)
   int32_t out_buf;                         // shared-memory tile buffer receiving the result, or -1
   int32_t in_buf[2];                       // kind == SRC_STACK: tile buffer holding the child
-  int32_t spill;                           // stored AND read back inside the same launch: plain stores
-  int32_t pushed;                          // out_buf is a stack slot (the result is popped by a later op)
+  int32_t spill;                           // bit 0: stored AND read back inside the same launch (plain stores);
+                                           // bit 1: out_buf is a stack slot (the result is popped by a later op)
+  int32_t frec_out;                        // library record that must keep a copy of THIS op's two edges' P, or -1
   int32_t pf_buf;                          // >= 0: child 1 (SRC_STACK, src[1] = its stored partial) is prefetched into this tile buffer
 };
 static_assert(sizeof(OpDesc) == 256, "OpDesc must stay 256 bytes");

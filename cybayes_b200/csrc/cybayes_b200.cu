@@ -122,10 +122,14 @@ struct Snapshot {
   std::vector<int32_t> cherry_of_node;  // 2-state family: record of a folded cherry (never materialised), or -1
   int refs = 0;
 };
-// A folded cherry kept by a snapshot: its two tips and, in the library's own P pool at slots
-// [rec * 2C, (rec + 1) * 2C), copies of the P matrices of its two tip edges (tip 0: C slots, tip 1: C slots).
+// A small subtree kept by a snapshot as a RECORD instead of a stored partial: its two children and, in the library's own
+// P pool at slots [rec * 2C, (rec + 1) * 2C), copies of the P matrices of its two child edges (child 0: C slots, child 1:
+// C slots).  A cherry (both children tips) is folded into its parent's lookup table; a node whose children are tips or
+// cherries (3 or 4 tips below it; tiled kernel only) is recomputed on the fly when a later dirty path needs it as a
+// sibling -- two table look-ups and a product per site instead of 68 bytes of HBM per site.  child[k] <= n_taxa: a tip;
+// otherwise the node id of a cherry that the same snapshot holds as a record.
 struct CherryRec {
-  int32_t tip[2] = {0, 0};
+  int32_t tip[2] = {0, 0};   // (children; named tip for the common case)
   int refs = 0;
 };
 
@@ -135,7 +139,8 @@ struct PlanChild {
   int32_t ref;   // SRC_TIP: tip id.  SRC_BUFFER: position of the producing op, or ~node (< 0) when the input snapshot
                  // holds it.  SRC_CHERRY: caller's op index of the folded cherry, or ~node for a record of the input
                  // snapshot.  SRC_STACK: tile buffer.  SRC_CARRIED: unused.
-  int32_t edge;  // 2 * (caller's op index) + child: where this edge's P slots sit in the caller's arrays
+  int32_t edge;  // 2 * (caller's op index) + child: where this edge's P slots sit in the caller's arrays; < 0: the edge
+                 // belongs to a record of the input snapshot, its P copies start at library slot ~edge
 };
 struct PlanOp {
   int32_t node;
@@ -143,6 +148,8 @@ struct PlanOp {
   int32_t out_buf;               // tiled kernel: shared-memory tile buffer of the result, or -1
   int32_t pf_buf;                // tiled kernel: tile buffer a stored child is prefetched into, or -1
   uint8_t is_root, keep, stream, spill, pushed;
+  uint8_t make_rec;              // not stored: the returned snapshot keeps the node as a record (small subtree)
+  uint8_t synthetic;             // not in the caller's list: a record of the input snapshot recomputed as a sibling
 };
 struct PlanLaunch { int r_begin, r_end, max_ops, n_bufs; };
 struct EvalPlan {
@@ -154,7 +161,7 @@ struct EvalPlan {
   std::vector<RangeDesc> ranges;
   std::vector<PlanLaunch> launches;
   int64_t bytes_written = 0, bytes_read = 0;
-  int n_stored = 0, n_buffer_reads = 0, n_stack = 0, n_spills = 0, n_cherries = 0;
+  int n_stored = 0, n_buffer_reads = 0, n_stack = 0, n_spills = 0, n_cherries = 0, n_small_recs = 0;
   uint64_t stamp = 0;
 };
 constexpr int PLAN_FLAG_MASK = CB_EVAL_WANT_SNAPSHOT | CB_EVAL_STORE_ROOT | CB_EVAL_FORCE_LEVELS | CB_EVAL_FORCE_WALK | CB_EVAL_NO_FOLD;
@@ -179,6 +186,7 @@ struct cb_ctx {
   int s2t_minb = 2;       // resident blocks per SM it is launched for (2: 128 registers, 4-stage image ring; 3: 85, 3-stage)
   bool s2t_bulk = false;  // stored partials leave through staging tiles + bulk-async copies instead of plain stores
   bool s2t_prefetch = true;  // stored siblings of a carried child arrive through cp.async two ops ahead (dirty paths)
+  bool s2t_small_recs = true;  // nodes whose children are tips / cherries are kept as records, not stored
   S2TImage* d_images = nullptr;  // op images of the current evaluation (s2t_image_kernel)
   int s2_vec = 1;  // sites per thread of the 2-state kernel on large alignments
   int s2_minb = 3; // its __launch_bounds__ min blocks per SM (experiment knob)
@@ -316,6 +324,7 @@ static int create_impl(int device, cb_ctx** out) {
   if (const char* v = getenv("CYBAYES_S2T_MINB")) c->s2t_minb = atoi(v) == 3 ? 3 : 2;
   if (getenv("CYBAYES_S2T_BULK")) c->s2t_bulk = atoi(getenv("CYBAYES_S2T_BULK")) != 0;
   if (getenv("CYBAYES_S2T_PREFETCH")) c->s2t_prefetch = atoi(getenv("CYBAYES_S2T_PREFETCH")) != 0;
+  if (getenv("CYBAYES_S2T_SMALL_RECS")) c->s2t_small_recs = atoi(getenv("CYBAYES_S2T_SMALL_RECS")) != 0;
   c->s2t_slots = c->s2t_minb == 3 ? 3 : 4;
   if (const char* v = getenv("CYBAYES_S2T_SLOTS")) c->s2t_slots = std::max(0, std::min(8, atoi(v)));
   if (getenv("CYBAYES_NO_PLAN_CACHE")) c->no_plan_cache = true;
@@ -738,7 +747,7 @@ static int snapshot_read_impl(cb_ctx* c, int s, int node, double* out, int32_t* 
 extern "C" int cb_snapshot_read(cb_ctx* c, int s, int node, double* out, int32_t* scale_out) {
   return guarded([&] { return snapshot_read_impl(c, s, node, out, scale_out); });
 }
-static int materialize_cherry(cb_ctx* c, int rec, int* buf_out);
+static int materialize_cherry(cb_ctx* c, const Snapshot& sn, int rec, int* buf_out);
 static int snapshot_read_impl(cb_ctx* c, int s, int node, double* out, int32_t* scale_out) {
   REQUIRE(c && out && snapshot_valid(c, s), "invalid snapshot %d", s);
   const Snapshot& sn = c->snaps[s];
@@ -747,7 +756,7 @@ static int snapshot_read_impl(cb_ctx* c, int s, int node, double* out, int32_t* 
   int bidx = sn.buf_of_node[node], tmp_buf = -1;
   if (bidx < 0 && node < (int)sn.cherry_of_node.size() && sn.cherry_of_node[node] >= 0) {
     // a folded cherry has no stored partial: compute it now, from the P copies the snapshot keeps
-    if (materialize_cherry(c, sn.cherry_of_node[node], &tmp_buf)) return 1;
+    if (materialize_cherry(c, sn, sn.cherry_of_node[node], &tmp_buf)) return 1;
     bidx = tmp_buf;
   }
   REQUIRE(bidx >= 0, "node %d is not in snapshot %d", node, s);
@@ -978,10 +987,11 @@ static int launch_images(cb_ctx* c, const LaunchConst& k, int n_ops) {
   return 0;
 }
 
-// Compute the partial of a folded cherry into a fresh buffer (debug / read-back path): one ordinary op
-// with two tip children whose P matrices come from the library's pool.
-static int materialize_cherry(cb_ctx* c, int rec, int* buf_out) {
-  REQUIRE(c->family_s2 && rec >= 0 && rec < (int)c->recs.size(), "bad cherry record %d", rec);
+// Compute the partial of a node that a snapshot keeps as a record (a folded cherry or a small subtree) into a fresh
+// buffer (debug / read-back path): one ordinary op whose P matrices come from the library's pool; a child that is itself
+// a cherry record of the same snapshot is looked up in its table, as in a normal evaluation.
+static int materialize_cherry(cb_ctx* c, const Snapshot& sn, int rec, int* buf_out) {
+  REQUIRE(c->family_s2 && rec >= 0 && rec < (int)c->recs.size(), "bad record %d", rec);
   if (ensure_staging(c, 1, 1, 1)) return 1;
   CU(cudaStreamSynchronize(c->stream));
   int bi;
@@ -990,13 +1000,27 @@ static int materialize_cherry(cb_ctx* c, int rec, int* buf_out) {
   memset(&op, 0, sizeof op);
   op.dst = c->buffers[bi].data;
   op.dst_scale = c->buffers[bi].scale;
-  op.out_buf = op.pf_buf = -1;
-  op.pushed = 0;
-  for (int kx = 0; kx < 2; ++kx) {
-    op.kind[kx] = SRC_TIP;
-    op.src[kx] = (const char*)c->d_codes + (size_t)(c->recs[rec].tip[kx] - 1) * c->P * c->code_bytes;
-    for (int q = 0; q < c->n_cats; ++q) op.pslot[kx][q] = CB_LIB_SLOT | (rec * 2 * c->n_cats + kx * c->n_cats + q);
-    op.crec_out[kx] = -1;
+  op.out_buf = op.pf_buf = op.frec_out = -1;
+  const int C = c->n_cats, N = c->n_taxa;
+  const size_t row_bytes = (size_t)c->P * c->code_bytes;
+  int order[2] = {0, 1};
+  if (c->s2_tiled && c->recs[rec].tip[0] > N && c->recs[rec].tip[1] <= N) { order[0] = 1; order[1] = 0; }  // canonical: tip first
+  for (int w = 0; w < 2; ++w) {
+    const int kx = order[w], ch = c->recs[rec].tip[kx];
+    for (int q = 0; q < C; ++q) op.pslot[w][q] = CB_LIB_SLOT | (rec * 2 * C + kx * C + q);
+    op.crec_out[w] = -1;
+    if (ch <= N) {
+      op.kind[w] = SRC_TIP;
+      op.src[w] = (const char*)c->d_codes + (size_t)(ch - 1) * row_bytes;
+    } else {
+      const int yrec = ch < (int)sn.cherry_of_node.size() ? sn.cherry_of_node[ch] : -1;
+      if (yrec < 0) { buffer_release(c, bi); return fail("internal error: cherry %d of record %d is not in the snapshot", ch, rec); }
+      op.kind[w] = SRC_CHERRY;
+      for (int t = 0; t < 2; ++t) {
+        op.ctip[w][t] = (const char*)c->d_codes + (size_t)(c->recs[yrec].tip[t] - 1) * row_bytes;
+        for (int q = 0; q < CB_S2_MAX_CATS; ++q) op.cslot[w][t][q] = q < C ? (CB_LIB_SLOT | (yrec * 2 * C + t * C + q)) : 0;
+      }
+    }
   }
   *reinterpret_cast<RangeDesc*>(c->h_stage + sizeof(OpDesc)) = RangeDesc{0, 1, -1, 0};
   CU(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof(OpDesc) + sizeof(RangeDesc), cudaMemcpyHostToDevice, c->stream));
@@ -1034,11 +1058,12 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
   const bool fold = c->family_s2 && !(flags & CB_EVAL_NO_FOLD);
   const bool want_snap = (flags & CB_EVAL_WANT_SNAPSHOT) != 0;
   const bool store_root = (flags & CB_EVAL_STORE_ROOT) != 0;
+  const int C = c->n_cats;
   const int K = c->s2_tiled ? c->s2t_slots : 0;  // stack slots of the kernel
   const int slot_base = c->s2t_bulk ? S2T_STAGING : 0;  // tile buffers below it are the staging buffers of the bulk-store path
   plan.ops.clear(); plan.ranges.clear(); plan.launches.clear();
   plan.bytes_written = plan.bytes_read = 0;
-  plan.n_stored = plan.n_buffer_reads = plan.n_stack = plan.n_spills = plan.n_cherries = 0;
+  plan.n_stored = plan.n_buffer_reads = plan.n_stack = plan.n_spills = plan.n_cherries = plan.n_small_recs = 0;
   const int64_t tip_row_bytes = c->P * c->code_bytes;
 
   struct LOp { int32_t node, caller; int32_t child[2], folded[2]; };
@@ -1083,6 +1108,29 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
         o.folded[kx] = ch > N ? folded_at[ch] : -1;
       }
       L.push_back(o);
+    }
+    // Children that the input snapshot holds as records of small subtrees (not cherries) are recomputed here: one
+    // synthetic op each, placed before the caller's ops; the walk pushes / carries its result like any other child.
+    if (sin && c->s2_tiled) {
+      std::vector<LOp> syn;
+      auto is_rec = [&](int nd) { return nd > N && nd < (int)sin->cherry_of_node.size() && sin->cherry_of_node[nd] >= 0; };
+      for (const LOp& o : L)
+        for (int kx = 0; kx < 2; ++kx) {
+          const int ch = o.child[kx];
+          if (ch <= N || o.folded[kx] >= 0 || !is_rec(ch)) continue;
+          const CherryRec& r = c->recs[sin->cherry_of_node[ch]];
+          if (r.tip[0] <= N && r.tip[1] <= N) continue;   // a cherry: folded into the parent's table
+          bool in_list = false;
+          for (const LOp& q : L) in_list = in_list || q.node == ch;
+          if (in_list) continue;
+          LOp so;
+          so.node = ch;
+          so.caller = ~sin->cherry_of_node[ch];            // < 0: synthetic, names the record
+          so.child[0] = r.tip[0]; so.child[1] = r.tip[1];
+          so.folded[0] = so.folded[1] = -1;
+          syn.push_back(so);
+        }
+      if (!syn.empty()) L.insert(L.begin(), syn.begin(), syn.end());
     }
     const int n = (int)L.size();
     // producers of the children inside this list (-1: tip, folded cherry or snapshot)
@@ -1261,12 +1309,13 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
       po.node = L[j].node;
       po.is_root = (j == n - 1);
       REQUIRE(!po.is_root || p == n - 1, "internal error: root is not last");
-      po.keep = po.stream = po.spill = po.pushed = 0;
+      po.keep = po.stream = po.spill = po.pushed = po.make_rec = 0;
+      po.synthetic = L[j].caller < 0 ? 1 : 0;
       po.out_buf = po.pf_buf = -1;
       for (int kx = 0; kx < 2; ++kx) {
         PlanChild& pc = po.ch[kx];
         const int ch = L[j].child[kx];
-        pc.edge = 2 * L[j].caller + kx;
+        pc.edge = L[j].caller >= 0 ? 2 * L[j].caller + kx : ~((~L[j].caller) * 2 * C + kx * C);
         if (ch <= N) {
           pc.kind = SRC_TIP;
           pc.ref = ch;
@@ -1312,7 +1361,7 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
     for (int p = 0; p < n; ++p) {
       const int j = order[p];
       PlanOp& po = plan.ops[base + p];
-      po.keep = po.is_root ? (want_snap && store_root) : (want_snap || read_back[j] != 0);
+      po.keep = po.is_root ? (want_snap && store_root) : ((want_snap && !po.synthetic) || read_back[j] != 0);
       po.stream = (po.keep && read_back[j] == 0 && c->s2_stream_stores) ? 1 : 0;
       po.spill = (read_back[j] == 2) ? 1 : 0;
       if (po.keep) {
@@ -1320,19 +1369,29 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
         plan.n_stored++;
         if (po.spill) plan.n_spills++;
       }
+      // small subtrees (children: tips / cherries) are not stored: the returned snapshot keeps a record
+      if (c->s2_tiled && c->s2t_small_recs && want_snap && po.keep && !po.is_root && !po.synthetic && read_back[j] == 0 &&
+          (po.ch[0].kind == SRC_TIP || po.ch[0].kind == SRC_CHERRY) && po.ch[1].kind == SRC_CHERRY) {
+        po.keep = 0;
+        po.stream = 0;
+        po.make_rec = 1;
+        plan.bytes_written -= (int64_t)c->buffer_bytes;
+        plan.n_stored--;
+        plan.n_small_recs++;
+      }
       if (c->s2_tiled) {
         if (push_slot[j] >= 0 && !po.is_root) { po.out_buf = push_slot[j]; po.pushed = 1; }
         else if (c->s2t_bulk && po.keep && !po.spill) { po.out_buf = staging_rr; staging_rr ^= 1; }
       }
     }
-    bool uses_stack = false;
-    for (int j = 0; j < n; ++j) uses_stack = uses_stack || push_slot[j] >= 0;
-    if (c->s2_tiled && c->s2t_prefetch && !uses_stack && !c->s2t_bulk) {
-      // Dirty paths and other lists that need no stack: a stored partial that comes from the input snapshot (or an earlier
-      // launch) and is read beside a carried child is prefetched into a tile buffer two ops ahead (three rotating
-      // buffers) and then read like a stack slot: the path keeps three sibling tiles per warp in flight instead of
-      // exposing one DRAM latency per op.
-      const int pf_base = 0;
+    int max_slot = -1;
+    for (int j = 0; j < n; ++j) max_slot = std::max(max_slot, push_slot[j]);
+    if (c->s2_tiled && c->s2t_prefetch && max_slot < 2 && !c->s2t_bulk) {
+      // Dirty paths and other lists with a shallow stack: a stored partial that comes from the input snapshot (or an
+      // earlier launch) and is read beside a carried child is prefetched into a tile buffer two ops ahead (three rotating
+      // buffers above the stack slots in use) and then read like a stack slot: the path keeps three sibling tiles per
+      // warp in flight instead of exposing one DRAM latency per op.
+      const int pf_base = max_slot + 1;
       int rr = 0;
       for (int p = 0; p < n; ++p) {
         PlanOp& po = plan.ops[base + p];
@@ -1505,8 +1564,8 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
     OpDesc& op = h_ops[p];
     op.is_root = po.is_root;
     op.pad_ = po.stream;
-    op.spill = po.spill;
-    op.pushed = po.pushed;
+    op.spill = (po.spill ? 1 : 0) | (po.pushed ? 2 : 0);
+    op.frec_out = -1;
     op.pf_buf = po.pf_buf;
     op.out_buf = po.out_buf;
     op.dst = nullptr;
@@ -1530,8 +1589,12 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
       op.ctip[kx][0] = op.ctip[kx][1] = nullptr;
       op.crec_out[kx] = -1;
       op.in_buf[kx] = -1;
-      const int32_t* ps = pslots_in + (size_t)pc.edge * C;
-      for (int q = 0; q < C; ++q) op.pslot[kx][q] = ps[q];
+      if (pc.edge >= 0) {
+        const int32_t* ps = pslots_in + (size_t)pc.edge * C;
+        for (int q = 0; q < C; ++q) op.pslot[kx][q] = ps[q];
+      } else {  // an edge of a record of the input snapshot: its P copies live in the library's pool
+        for (int q = 0; q < C; ++q) op.pslot[kx][q] = CB_LIB_SLOT | (~pc.edge + q);
+      }
       for (int q = C; q < CB_MAX_CATS; ++q) op.pslot[kx][q] = 0;
       switch (pc.kind) {
         case SRC_TIP:
@@ -1581,6 +1644,18 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
           break;
         default: break;
       }
+    }
+    if (po.make_rec) {  // the node stays in the returned snapshot as a record: children (tip ids / cherry node ids) + P copies
+      int ids[2];
+      for (int kx = 0; kx < 2; ++kx) {
+        const PlanChild& pc = po.ch[kx];
+        ids[kx] = pc.kind == SRC_TIP ? pc.ref : (pc.ref >= 0 ? nodes_in[pc.ref] : ~pc.ref);
+      }
+      int r;
+      if (rec_acquire(c, ids[0], ids[1], &r)) return 1;
+      guard.recs.push_back(r);
+      op.frec_out = r;
+      new_cherry_nodes.push_back(po.node);
     }
   }
   memcpy(c->h_stage + off_ranges, plan->ranges.data(), (size_t)n_ranges * sizeof(RangeDesc));
@@ -1658,7 +1733,7 @@ static int eval_impl(cb_ctx* c, int snapshot_in, int n_lists, const int32_t* off
   c->last_bytes_read = plan->bytes_read;
   c->last_counts[0] = total_ops; c->last_counts[1] = plan->n_stored; c->last_counts[2] = plan->n_buffer_reads;
   c->last_counts[3] = plan->n_stack; c->last_counts[4] = plan->n_spills; c->last_counts[5] = plan->n_cherries;
-  c->last_counts[6] = (int)plan->launches.size(); c->last_counts[7] = (int)c->plan_builds;
+  c->last_counts[6] = (int)plan->launches.size(); c->last_counts[7] = plan->n_small_recs;
 
   if (c->comm && !fused) {
     int r = g_nccl.AllReduce(c->d_results, c->d_results, (size_t)n_lists, NCCL_DOUBLE, NCCL_SUM, c->comm, c->stream);

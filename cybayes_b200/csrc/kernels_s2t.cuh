@@ -168,16 +168,23 @@ __global__ void __launch_bounds__(32) s2t_image_kernel(const LaunchConst k, int 
     im->out_buf = op->out_buf;
     im->in_buf[0] = op->in_buf[0]; im->in_buf[1] = op->in_buf[1];
     // out_buf names a stack slot (the op is pushed) or a staging buffer of the bulk-store path
-    const bool stored = op->dst != nullptr, pushed = op->pushed != 0, staged = op->out_buf >= 0 && !pushed;
+    const bool stored = op->dst != nullptr, pushed = (op->spill & 2) != 0, staged = op->out_buf >= 0 && !pushed;
+    const bool spill = (op->spill & 1) != 0;
     int mode = pushed ? S2T_ST_SMEM : S2T_ST_NONE;
     if (stored) {
-      if (staged || (pushed && k.s2t_bulk && !op->spill)) mode |= S2T_ST_BULK;
+      if (staged || (pushed && k.s2t_bulk && !spill)) mode |= S2T_ST_BULK;
       else mode |= S2T_ST_GLOBAL | (op->pad_ ? S2T_ST_STREAM : 0);
     }
     im->store_mode = mode;
     im->pf_buf = op->pf_buf;
     im->pad_ = 0;
   }
+  // a small subtree that stays in the returned cache as a record (never stored) keeps copies of its two edges' P
+  if (op->frec_out >= 0)
+    for (int idx = t; idx < 2 * C * 4; idx += 32) {
+      const int e = idx & 3, c = (idx >> 2) % C, ch = idx / (4 * C);
+      k.pmats_lib[((int64_t)op->frec_out * 2 * C + ch * C + c) * 4 + e] = __ldg(s2_pmat(k, op->pslot[ch][c]) + e);
+    }
   // P matrices of internal and tip children (one thread per child, category and row)
   for (int idx = t; idx < 4 * C; idx += 32) {
     const int i = idx & 1, c = (idx >> 1) % C, ch = idx / (2 * C);

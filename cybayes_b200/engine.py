@@ -241,7 +241,7 @@ class Engine(SlotPool):
         w, r = C.c_int64(), C.c_int64()
         counts = np.zeros(8, dtype=np.int32)
         check(self._lib.cb_last_eval_info(self._ctx, C.byref(w), C.byref(r), _i32(counts)))
-        names = ("ops", "stored", "read_back", "stack_pops", "spills", "cherries_folded", "launches", "plans_built")
+        names = ("ops", "stored", "read_back", "stack_pops", "spills", "cherries_folded", "launches", "small_records")
         out = dict(zip(names, (int(x) for x in counts)))
         out["bytes_written"], out["bytes_read"] = w.value, r.value
         return out

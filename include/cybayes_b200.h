@@ -191,7 +191,8 @@ int cb_last_eval_main_ms(cb_ctx* ctx, float* ms_out);
 /* What the last evaluation had to move, from its op list: bytes of partials (+ exponents) it stored, bytes it
  * read (stored partials read back, tip codes, pattern weights) -- the roofline numerator of bench.py -- and
  * counts8 = { ops run, partials stored, partials read back, children popped from the shared-memory stack,
- * partials stored and re-read inside one launch, cherries folded, pruning launches, plans built so far }. */
+ * partials stored and re-read inside one launch, cherries folded, pruning launches, small subtrees (children: tips /
+ * cherries) kept as records instead of stored partials }. */
 int cb_last_eval_info(cb_ctx* ctx, int64_t* bytes_written, int64_t* bytes_read, int32_t* counts8);
 /* host microseconds cb_eval / cb_eval_batch have spent since the last reset, by phase: us6 = { plan look-up or build,
  * descriptor fill, upload + launches, wait for the result, snapshot bookkeeping, number of calls } */

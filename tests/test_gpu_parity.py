@@ -612,9 +612,11 @@ def test_tiled_two_state_kernel_small_inputs(n_taxa, n_sites, model, slots, n_ca
     assert abs(l1 - l0) <= 1e-13 * abs(l0)
     for n in p1:
         assert np.array_equal(p1[n][0], p0[n][0]) and np.array_equal(p1[n][1], p0[n][1]), n
-    assert i1["stored"] == i0["stored"] and i1["bytes_written"] == i0["bytes_written"]
+    # the tiled kernel keeps small subtrees (children: tips / cherries) as records instead of stored partials
+    assert i1["stored"] + i1["small_records"] == i0["stored"] and i0["small_records"] == 0
+    assert i1["bytes_written"] <= i0["bytes_written"]
     if slots > 0 and n_taxa > 8:
-        assert i1["stack_pops"] > 0 and i1["read_back"] <= i0["read_back"]
+        assert i1["stack_pops"] > 0 and i1["read_back"] <= i0["read_back"] and i1["small_records"] > 0
 
 
 @pytest.mark.parametrize("name", ["narrow_F81", "ielex_multistate_F81", "phon_ringe_GTR"])
