@@ -182,8 +182,11 @@ struct cb_ctx {
   double* d_staged = nullptr;  // P matrices of the current evaluation in stage layout and consumption order
   size_t staged_bytes = 0;
   bool s2_tiled = false;  // 2-state family on a large alignment: tile-interleaved partials + prune_s2t_kernel
-  int s2t_slots = 4;      // its shared-memory stack slots per warp
-  int s2t_minb = 2;       // resident blocks per SM it is launched for (2: 128 registers, 4-stage image ring; 3: 85, 3-stage)
+  int s2t_slots = 3;      // its shared-memory stack slots per tile
+  int s2t_minb = 3;       // resident blocks per SM it is launched for (2: 4-stage image ring, up to 4 slots; 3: 3-stage ring,
+                          // 3 slots).  Measured on C4 (profiles/README.md): V = 2 with 3 blocks 6.17 ms, V = 1 with 3 blocks
+                          // 6.56 ms, V = 1 with 2 blocks and 4 slots 7.10 ms, V = 2 with 2 blocks 7.84 ms, 4 blocks 7.0 ms
+  int s2t_v = 2;          // tiles per warp (2: 4 warps per block, each handling two 32-site tiles; 1: 8 warps, one tile each)
   bool s2t_bulk = false;  // stored partials leave through staging tiles + bulk-async copies instead of plain stores
   bool s2t_prefetch = true;  // stored siblings of a carried child arrive through cp.async two ops ahead (dirty paths)
   bool s2t_small_recs = true;  // nodes whose children are tips / cherries are kept as records, not stored
@@ -321,16 +324,19 @@ static int create_impl(int device, cb_ctx** out) {
   if (const char* v = getenv("CYBAYES_S2_V")) c->s2_vec = (atoi(v) == 2) ? 2 : 1;
   if (const char* v = getenv("CYBAYES_S2_MINB")) c->s2_minb = (atoi(v) == 4) ? 4 : 3;
   if (getenv("CYBAYES_S2_NO_CS")) c->s2_stream_stores = false;
-  if (const char* v = getenv("CYBAYES_S2T_MINB")) c->s2t_minb = atoi(v) == 3 ? 3 : 2;
+  if (const char* v = getenv("CYBAYES_S2T_MINB")) c->s2t_minb = std::max(2, std::min(4, atoi(v)));
+  if (const char* v = getenv("CYBAYES_S2T_V")) c->s2t_v = atoi(v) == 2 ? 2 : 1;
+  if (c->s2t_minb == 4) c->s2t_v = 1;
   if (getenv("CYBAYES_S2T_BULK")) c->s2t_bulk = atoi(getenv("CYBAYES_S2T_BULK")) != 0;
   if (getenv("CYBAYES_S2T_PREFETCH")) c->s2t_prefetch = atoi(getenv("CYBAYES_S2T_PREFETCH")) != 0;
   if (getenv("CYBAYES_S2T_SMALL_RECS")) c->s2t_small_recs = atoi(getenv("CYBAYES_S2T_SMALL_RECS")) != 0;
-  c->s2t_slots = c->s2t_minb == 3 ? 3 : 4;
+  c->s2t_slots = c->s2t_minb == 4 ? 2 : c->s2t_minb == 3 ? 3 : 4;
   if (const char* v = getenv("CYBAYES_S2T_SLOTS")) c->s2t_slots = std::max(0, std::min(8, atoi(v)));
   if (getenv("CYBAYES_NO_PLAN_CACHE")) c->no_plan_cache = true;
   if (const char* v = getenv("CYBAYES_MAX_DEVICE_BYTES")) c->max_dev_bytes = atoll(v);
-#define CB_S2T_ATTR(CC, MB) CU(cudaFuncSetAttribute(prune_s2t_kernel<CC, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024))
-  CB_S2T_ATTR(4, 2); CB_S2T_ATTR(4, 3); CB_S2T_ATTR(1, 2); CB_S2T_ATTR(1, 3);   // + 384 B static each
+#define CB_S2T_ATTR(CC, MB, VV) CU(cudaFuncSetAttribute(prune_s2t_kernel<CC, MB, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024))
+  CB_S2T_ATTR(4, 2, 1); CB_S2T_ATTR(4, 3, 1); CB_S2T_ATTR(1, 2, 1); CB_S2T_ATTR(1, 3, 1);   // + 384 B static each
+  CB_S2T_ATTR(4, 2, 2); CB_S2T_ATTR(1, 2, 2); CB_S2T_ATTR(4, 3, 2); CB_S2T_ATTR(1, 3, 2); CB_S2T_ATTR(4, 4, 1); CB_S2T_ATTR(1, 4, 1);
 #undef CB_S2T_ATTR
   CU(cudaFuncSetAttribute(prune_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #define CB_DMMA_ATTR(SS) CU(cudaFuncSetAttribute(prune_dmma_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
@@ -922,10 +928,18 @@ static int launch_ranges(cb_ctx* c, const LaunchConst& k, int r_begin, int r_end
     REQUIRE(smem <= (size_t)226 * 1024, "internal error: %d tile buffers do not fit shared memory", n_bufs);
     const int64_t n_tiles = c->P / S2T_W;
     dim3 grid((unsigned)((n_tiles + S2T_WARPS - 1) / S2T_WARPS), (unsigned)n_r);
-    if (c->n_cats == 4 && c->s2t_minb == 3) prune_s2t_kernel<4, 3><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
-    else if (c->n_cats == 4) prune_s2t_kernel<4, 2><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
-    else if (c->s2t_minb == 3) prune_s2t_kernel<1, 3><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
-    else prune_s2t_kernel<1, 2><<<grid, S2T_THREADS, smem, c->stream>>>(kk, c->d_images, n_bufs);
+    // V tiles per warp (8 / V warps per block): fixed per context, so every evaluation of an alignment sums in one order
+#define CB_S2T_LAUNCH(MB, VV)                                                                                              \
+  do {                                                                                                                     \
+    if (c->n_cats == 4) prune_s2t_kernel<4, MB, VV><<<grid, S2T_THREADS / VV, smem, c->stream>>>(kk, c->d_images, n_bufs); \
+    else prune_s2t_kernel<1, MB, VV><<<grid, S2T_THREADS / VV, smem, c->stream>>>(kk, c->d_images, n_bufs);                \
+  } while (0)
+    if (c->s2t_v == 2 && c->s2t_minb >= 3) CB_S2T_LAUNCH(3, 2);
+    else if (c->s2t_v == 2) CB_S2T_LAUNCH(2, 2);
+    else if (c->s2t_minb == 4) CB_S2T_LAUNCH(4, 1);
+    else if (c->s2t_minb == 3) CB_S2T_LAUNCH(3, 1);
+    else CB_S2T_LAUNCH(2, 1);
+#undef CB_S2T_LAUNCH
   } else if (c->family_s2) {
     // Fixed per alignment (independent of the schedule) so the reduction order never changes:
     // 64-thread blocks, one site per thread, to spread a small alignment over the SMs (the tiled kernel above

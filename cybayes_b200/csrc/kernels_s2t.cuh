@@ -30,8 +30,8 @@
 
 namespace cb {
 
-constexpr int S2T_W = 32;          // sites per tile (one warp)
-constexpr int S2T_WARPS = 8;       // warps per block
+constexpr int S2T_W = 32;          // sites per tile
+constexpr int S2T_WARPS = 8;       // tiles per block (a warp owns V consecutive tiles: 8 / V warps per block)
 constexpr int S2T_THREADS = S2T_W * S2T_WARPS;
 constexpr int S2T_RING_OPS = 4;    // op images per ring chunk
 __host__ __device__ constexpr int s2t_ring_stages(int minb) { return minb >= 3 ? 3 : 4; }  // chunks in the ring: a refill has
@@ -83,7 +83,7 @@ enum S2TStore : int32_t {
   S2T_ST_BULK = 8      // through a tile buffer in shared memory (out_buf) and one bulk-async copy (CYBAYES_S2T_BULK=1)
 };
 
-constexpr int S2T_CODE_SLOTS = 4;  // per warp: tip codes of 4 consecutive ops (4 rows x 32 sites x 1 byte each), cp.async ring
+constexpr int S2T_CODE_SLOTS = 4;  // per tile: tip codes of 4 consecutive ops (4 rows x 32 sites x 1 byte each), cp.async ring
 constexpr int S2T_CODE_BYTES = S2T_CODE_SLOTS * 4 * S2T_W;
 
 __host__ __device__ inline size_t s2t_smem_bytes(int n_bufs, int C, int minb) {
@@ -132,6 +132,9 @@ __device__ __forceinline__ void s2t_fence_async_smem() { asm volatile("fence.pro
 // 4-byte asynchronous copy global -> shared (LDGSTS): no destination register, completion tracked per thread in groups
 __device__ __forceinline__ void s2t_cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s2t_smem_addr(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void s2t_cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s2t_smem_addr(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void s2t_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void s2t_cp_async16(void* smem, const void* gmem) {
@@ -251,88 +254,110 @@ __global__ void __launch_bounds__(32) s2t_image_kernel(const LaunchConst k, int 
 }
 
 // ---------------------------------------------------------------------------------------- main kernel
+// A warp owns V consecutive tiles (V = 2 by default: lane l handles site l of either tile).  Everything that does not
+// depend on the site -- the op image, the jump to the op body, the broadcast loads of the P rows, pointer arithmetic,
+// the ring and code pipelines -- is done once for both tiles, and the two sites' dependency chains interleave.
+//
 // contribution of one child to the op's product: FIRST initialises acc, the second child multiplies into it.
-// codes: this op's slot of the warp's code ring, [row q][site]: child 0 uses rows 0, 1, child 1 rows 2, 3.
-template <int C, int KIND, int CH, bool FIRST>
-__device__ __forceinline__ void s2t_child(const S2TImage& im, const double (&cur)[C][2], int cur_e, const unsigned char* codes,
-                                          const unsigned char* mybufs, size_t tile_off, int lane, double (&acc)[C][2], int& e_in) {
+// codes: this op's slot of the warp's code ring, [row q][V * 32 sites]: child 0 uses rows 0, 1, child 1 rows 2, 3.
+template <int C, int V, int KIND, int CH, bool FIRST>
+__device__ __forceinline__ void s2t_child(const S2TImage& im, const double (&cur)[V][C][2], const int (&cur_e)[V],
+                                          const unsigned char* codes, const unsigned char* mybufs, size_t tile_off, int lane,
+                                          double (&acc)[V][C][2], int (&e_in)[V]) {
   constexpr int TB = s2t_tile_bytes(C);
   const double* pbase = &im.tab[CH][0];
   if constexpr (KIND == SRC_CARRIED || KIND == SRC_STACK || KIND == SRC_BUFFER) {
-    double L[C][2];
-    int se;
-    if constexpr (KIND == SRC_CARRIED) {
+    double L[V][C][2];
+    int se[V];
 #pragma unroll
-      for (int c = 0; c < C; ++c) { L[c][0] = cur[c][0]; L[c][1] = cur[c][1]; }
-      se = cur_e;
-    } else if constexpr (KIND == SRC_STACK) {
-      const double* sb = reinterpret_cast<const double*>(mybufs + (size_t)im.in_buf[CH] * TB);
+    for (int v = 0; v < V; ++v) {
+      if constexpr (KIND == SRC_CARRIED) {
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        L[c][0] = sb[(2 * c) * S2T_W + lane];
-        L[c][1] = sb[(2 * c + 1) * S2T_W + lane];
+        for (int c = 0; c < C; ++c) { L[v][c][0] = cur[v][c][0]; L[v][c][1] = cur[v][c][1]; }
+        se[v] = cur_e[v];
+      } else if constexpr (KIND == SRC_STACK) {
+        const double* sb = reinterpret_cast<const double*>(mybufs + ((size_t)im.in_buf[CH] * V + v) * TB);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          L[v][c][0] = sb[(2 * c) * S2T_W + lane];
+          L[v][c][1] = sb[(2 * c + 1) * S2T_W + lane];
+        }
+        se[v] = reinterpret_cast<const int*>(sb + 2 * C * S2T_W)[lane];
+      } else {
+        const double* gb = reinterpret_cast<const double*>(im.src[CH] + tile_off + (size_t)v * TB);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          L[v][c][0] = __ldcg(gb + (2 * c) * S2T_W + lane);
+          L[v][c][1] = __ldcg(gb + (2 * c + 1) * S2T_W + lane);
+        }
+        se[v] = __ldcg(reinterpret_cast<const int*>(gb + 2 * C * S2T_W) + lane);
       }
-      se = reinterpret_cast<const int*>(sb + 2 * C * S2T_W)[lane];
-    } else {
-      const double* gb = reinterpret_cast<const double*>(im.src[CH] + tile_off);
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        L[c][0] = __ldcg(gb + (2 * c) * S2T_W + lane);
-        L[c][1] = __ldcg(gb + (2 * c + 1) * S2T_W + lane);
-      }
-      se = __ldcg(reinterpret_cast<const int*>(gb + 2 * C * S2T_W) + lane);
     }
-    const double2* pm = reinterpret_cast<const double2*>(pbase);   // (P[i][0], P[i][1]) broadcasts
+    const double2* pm = reinterpret_cast<const double2*>(pbase);   // (P[i][0], P[i][1]) broadcasts, shared by the V sites
 #pragma unroll
     for (int c = 0; c < C; ++c) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const double2 pr = pm[c * 2 + i];
-        const double x = fma(pr.y, L[c][1], pr.x * L[c][0]);      // v[i] = P[i][0] L[0] + P[i][1] L[1]
-        if (FIRST) acc[c][i] = x; else acc[c][i] *= x;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const double x = fma(pr.y, L[v][c][1], pr.x * L[v][c][0]);      // v[i] = P[i][0] L[0] + P[i][1] L[1]
+          if (FIRST) acc[v][c][i] = x; else acc[v][c][i] *= x;
+        }
       }
     }
-    if (FIRST) e_in = se; else e_in += se;
+#pragma unroll
+    for (int v = 0; v < V; ++v) { if (FIRST) e_in[v] = se[v]; else e_in[v] += se[v]; }
   } else if constexpr (KIND == SRC_TIP) {
     // state code 0 / 1 / 2 ('?', '-', '0/1') selects the staged contribution of this edge
-    const double* row = pbase + min((unsigned)codes[(2 * CH) * S2T_W + lane], 2u);
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
+    for (int v = 0; v < V; ++v) {
+      const double* row = pbase + min((unsigned)codes[(2 * CH) * (S2T_W * V) + v * S2T_W + lane], 2u);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const double x = row[(c * 2 + i) * 4];
-        if (FIRST) acc[c][i] = x; else acc[c][i] *= x;
+      for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double x = row[(c * 2 + i) * 4];
+          if (FIRST) acc[v][c][i] = x; else acc[v][c][i] *= x;
+        }
       }
+      if (FIRST) e_in[v] = 0;
     }
-    if (FIRST) e_in = 0;
   } else {  // folded cherry: the pair of tip codes selects a precomputed row
-    const unsigned ca = min((unsigned)codes[(2 * CH) * S2T_W + lane], 2u), cb_ = min((unsigned)codes[(2 * CH + 1) * S2T_W + lane], 2u);
-    const double* tab = pbase + (ca * 3 + cb_) * (2 * C + 1);
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
+    for (int v = 0; v < V; ++v) {
+      const unsigned ca = min((unsigned)codes[(2 * CH) * (S2T_W * V) + v * S2T_W + lane], 2u);
+      const unsigned cb_ = min((unsigned)codes[(2 * CH + 1) * (S2T_W * V) + v * S2T_W + lane], 2u);
+      const double* tab = pbase + (ca * 3 + cb_) * (2 * C + 1);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const double x = tab[c * 2 + i];
-        if (FIRST) acc[c][i] = x; else acc[c][i] *= x;
+      for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double x = tab[c * 2 + i];
+          if (FIRST) acc[v][c][i] = x; else acc[v][c][i] *= x;
+        }
       }
+      if (FIRST) e_in[v] = (int)tab[2 * C]; else e_in[v] += (int)tab[2 * C];
     }
-    if (FIRST) e_in = (int)tab[2 * C]; else e_in += (int)tab[2 * C];
   }
 }
 
-template <int C, int K0, int K1>
-__device__ __forceinline__ void s2t_pair(const S2TImage& im, const double (&cur)[C][2], int cur_e, const unsigned char* codes,
-                                         const unsigned char* mybufs, size_t tile_off, int lane, double (&out)[C][2], int& e_in) {
-  s2t_child<C, K0, 0, true>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in);
-  s2t_child<C, K1, 1, false>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in);
+template <int C, int V, int K0, int K1>
+__device__ __forceinline__ void s2t_pair(const S2TImage& im, const double (&cur)[V][C][2], const int (&cur_e)[V],
+                                         const unsigned char* codes, const unsigned char* mybufs, size_t tile_off, int lane,
+                                         double (&out)[V][C][2], int (&e_in)[V]) {
+  s2t_child<C, V, K0, 0, true>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in);
+  s2t_child<C, V, K1, 1, false>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in);
 }
 
-// MINB: resident blocks per SM the kernel is compiled for (2: up to 128 registers, 3: up to 85)
-template <int C, int MINB>
-__global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const LaunchConst k, const S2TImage* __restrict__ images,
-                                                                       int n_bufs) {
+// MINB: resident blocks per SM the kernel is compiled for; V: tiles per warp (block = 8 / V warps)
+template <int C, int MINB, int V>
+__global__ void __launch_bounds__(S2T_THREADS / V, MINB) prune_s2t_kernel(const LaunchConst k, const S2TImage* __restrict__ images,
+                                                                           int n_bufs) {
   static_assert(C <= CB_S2_MAX_CATS, "2-state kernel supports at most CB_S2_MAX_CATS categories");
+  static_assert(V == 1 || V == 2, "one or two tiles per warp");
   constexpr int TB = s2t_tile_bytes(C);
+  constexpr int WARPS = S2T_WARPS / V;
   constexpr int S2T_RING_STAGES = s2t_ring_stages(MINB);
   constexpr int RING = S2T_RING_OPS * S2T_RING_STAGES;
   extern __shared__ __align__(128) unsigned char s2t_smem[];
@@ -347,13 +372,14 @@ __global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const Laun
   const S2TImage* __restrict__ gimg = images + rg.begin;
   S2TImage* ring = reinterpret_cast<S2TImage*>(s2t_smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* mycodes = s2t_smem + (size_t)RING * sizeof(S2TImage) + (size_t)warp * S2T_CODE_BYTES;
-  unsigned char* mybufs = s2t_smem + (size_t)RING * sizeof(S2TImage) + (size_t)S2T_WARPS * S2T_CODE_BYTES + (size_t)warp * n_bufs * TB;
+  unsigned char* mycodes = s2t_smem + (size_t)RING * sizeof(S2TImage) + (size_t)warp * V * S2T_CODE_BYTES;
+  unsigned char* mybufs = s2t_smem + (size_t)RING * sizeof(S2TImage) + (size_t)S2T_WARPS * S2T_CODE_BYTES +
+                          (size_t)warp * V * n_bufs * TB;
 
-  const int64_t n_tiles = k.n_sites / S2T_W;
-  const int64_t tile = (int64_t)blockIdx.x * S2T_WARPS + warp;
+  const int64_t n_tiles = k.n_sites / S2T_W;                      // a multiple of 2 (sites are padded to 64)
+  const int64_t tile = ((int64_t)blockIdx.x * WARPS + warp) * V;   // first of this warp's V tiles
   const int64_t tiles_left = n_tiles - (int64_t)blockIdx.x * S2T_WARPS;
-  const int n_active = tiles_left < S2T_WARPS ? (int)tiles_left : S2T_WARPS;   // warps of this block that own a tile
+  const int n_active = tiles_left < S2T_WARPS ? (int)((tiles_left + V - 1) / V) : WARPS;   // warps of this block that own tiles
   const bool active = warp < n_active;
   const int64_t site = tile * S2T_W + lane;
   const size_t tile_off = (size_t)tile * TB;
@@ -365,22 +391,24 @@ __global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const Laun
     s2t_mbar_expect_tx(&full_bar[b], bytes);
     s2t_bulk_g2s(ring + (size_t)b * S2T_RING_OPS, gimg + (size_t)c * S2T_RING_OPS, bytes, &full_bar[b]);
   };
-  // the warp's tip codes of op o: lane = 8 q + j copies bytes [4 j, 4 j + 4) of the tile's 32 codes of row q
-  const int64_t code_off = tile * S2T_W + 4 * (lane & 7);
+  // the warp's tip codes of op o: lane = 8 q + j copies bytes [4 V j, 4 V (j + 1)) of the 32 V codes of row q
+  const int64_t code_off = tile * S2T_W + 4 * V * (lane & 7);
   auto issue_codes = [&](int o) {
     const S2TImage& im = ring[o % RING];
-    s2t_cp_async4(mycodes + (o % S2T_CODE_SLOTS) * (4 * S2T_W) + 4 * lane, static_cast<const char*>(im.rows[lane >> 3]) + code_off);
+    unsigned char* dst = mycodes + (o % S2T_CODE_SLOTS) * (4 * S2T_W * V) + 4 * V * lane;
+    const char* src = static_cast<const char*>(im.rows[lane >> 3]) + code_off;
+    if constexpr (V == 1) s2t_cp_async4(dst, src); else s2t_cp_async8(dst, src);
   };
-  // a stored partial that op o reads as its second child: the warp's tile (TB bytes, contiguous) in 16-byte pieces
+  // a stored partial that op o reads as its second child: the warp's V tiles (V * TB bytes, contiguous) in 16-byte pieces
   auto issue_prefetch = [&](int o) {
     const S2TImage& im = ring[o % RING];
     if (im.pf_buf >= 0) {
       const char* src = im.src[1] + tile_off;
-      unsigned char* dst = mybufs + (size_t)im.pf_buf * TB;
+      unsigned char* dst = mybufs + (size_t)im.pf_buf * V * TB;
 #pragma unroll
-      for (int j = 0; j < (TB / 16 + 31) / 32; ++j) {
+      for (int j = 0; j < (V * TB / 16 + 31) / 32; ++j) {
         const int idx = lane + 32 * j;
-        if (idx < TB / 16) s2t_cp_async16(dst + 16 * idx, src + 16 * idx);
+        if (idx < V * TB / 16) s2t_cp_async16(dst + 16 * idx, src + 16 * idx);
       }
     }
   };
@@ -402,10 +430,14 @@ __global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const Laun
 
   double lnl = 0.0;
   if (active) {
-    double cur[C][2];  // carried partial
-    int cur_e = 0;
+    double cur[V][C][2];  // carried partial
+    int cur_e[V];
 #pragma unroll
-    for (int c = 0; c < C; ++c) cur[c][0] = cur[c][1] = 0.0;
+    for (int v = 0; v < V; ++v) {
+      cur_e[v] = 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) cur[v][c][0] = cur[v][c][1] = 0.0;
+    }
     bool groups_pending = false;
 
     // code pipeline: the copies of op o + 2 are issued at the end of op o; one commit group per op
@@ -425,13 +457,13 @@ __global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const Laun
       const S2TImage& im = ring[o % RING];
       s2t_cp_async_wait<1>();   // this op's codes have landed (the group of op o + 1 may still be in flight)
       __syncwarp();
-      const unsigned char* codes = mycodes + (o % S2T_CODE_SLOTS) * (4 * S2T_W);
+      const unsigned char* codes = mycodes + (o % S2T_CODE_SLOTS) * (4 * S2T_W * V);
 
-      double out[C][2];
-      int e_in;
+      double out[V][C][2];
+      int e_in[V];
       switch (im.combo) {
 #define CB_S2T_CASE(NAME, K0, K1) \
-  case NAME: s2t_pair<C, K0, K1>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in); break;
+  case NAME: s2t_pair<C, V, K0, K1>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in); break;
         CB_S2T_CASE(S2T_CARRIED_STACK, SRC_CARRIED, SRC_STACK)
         CB_S2T_CASE(S2T_CARRIED_BUFFER, SRC_CARRIED, SRC_BUFFER)
         CB_S2T_CASE(S2T_CARRIED_TIP, SRC_CARRIED, SRC_TIP)
@@ -442,60 +474,69 @@ __global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const Laun
         CB_S2T_CASE(S2T_TIP_TIP, SRC_TIP, SRC_TIP)
         CB_S2T_CASE(S2T_TIP_CHERRY, SRC_TIP, SRC_CHERRY)
         default:
-          s2t_pair<C, SRC_CHERRY, SRC_CHERRY>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in);
+          s2t_pair<C, V, SRC_CHERRY, SRC_CHERRY>(im, cur, cur_e, codes, mybufs, tile_off, lane, out, e_in);
           break;
 #undef CB_S2T_CASE
       }
 
       if (!im.is_root) {
         // exact power-of-two rescale: all entries are >= 0, so the max of the high words carries the exponent of the max
-        int mh = __double2hiint(out[0][0]);
 #pragma unroll
-        for (int c = 0; c < C; ++c) mh = max(mh, max(__double2hiint(out[c][0]), __double2hiint(out[c][1])));
-        const int be = (mh >> 20) & 0x7ff;
-        const int x = (be == 0 || be == 0x7ff) ? 0 : be - 1023;
-        const double f = pow2_neg(x);
+        for (int v = 0; v < V; ++v) {
+          int mh = __double2hiint(out[v][0][0]);
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          cur[c][0] = out[c][0] * f;
-          cur[c][1] = out[c][1] * f;
+          for (int c = 0; c < C; ++c) mh = max(mh, max(__double2hiint(out[v][c][0]), __double2hiint(out[v][c][1])));
+          const int be = (mh >> 20) & 0x7ff;
+          const int x = (be == 0 || be == 0x7ff) ? 0 : be - 1023;
+          const double f = pow2_neg(x);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            cur[v][c][0] = out[v][c][0] * f;
+            cur[v][c][1] = out[v][c][1] * f;
+          }
+          cur_e[v] = e_in[v] + x;
         }
-        cur_e = e_in + x;
       } else {
         // ll_p = sum_c (pi . L_c) / n_cats ; lnL += w_p * log(ll_p)      ML_gamma.pyx:38,40
         const double pi0 = __ldg(k.pi), pi1 = __ldg(k.pi + 1);
-        const double w = __ldg(k.weights + site);
         const double ln2 = 0.693147180559945309417232121458;
-        double s = 0.0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) s += fma(pi1, out[c][1], pi0 * out[c][0]) / k.cats;
-        if (w != 0.0) lnl += w * (log(s) + (double)e_in * ln2);
+        for (int v = 0; v < V; ++v) {
+          const double w = __ldg(k.weights + site + v * S2T_W);
+          double s = 0.0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {   // an (optionally) stored root partial is kept as computed, exponent e_in
-          cur[c][0] = out[c][0];
-          cur[c][1] = out[c][1];
+          for (int c = 0; c < C; ++c) s += fma(pi1, out[v][c][1], pi0 * out[v][c][0]) / k.cats;
+          if (w != 0.0) lnl += w * (log(s) + (double)e_in[v] * ln2);
+#pragma unroll
+          for (int c = 0; c < C; ++c) {   // an (optionally) stored root partial is kept as computed, exponent e_in
+            cur[v][c][0] = out[v][c][0];
+            cur[v][c][1] = out[v][c][1];
+          }
+          cur_e[v] = e_in[v];
         }
-        cur_e = e_in;
       }
 
       const int mode = im.store_mode;
       if (mode != S2T_ST_NONE) {
-        if (mode & S2T_ST_GLOBAL) {  // plain coalesced stores: the tile is one contiguous 2 KB piece of the buffer
-          double* gb = reinterpret_cast<double*>(im.dst + tile_off);
-          if (mode & S2T_ST_STREAM) {
+        if (mode & S2T_ST_GLOBAL) {  // plain coalesced stores: a tile is one contiguous 2 KB piece of the buffer
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-              __stcs(gb + (2 * c) * S2T_W + lane, cur[c][0]);
-              __stcs(gb + (2 * c + 1) * S2T_W + lane, cur[c][1]);
-            }
-            __stcs(reinterpret_cast<int*>(gb + 2 * C * S2T_W) + lane, cur_e);
-          } else {
+          for (int v = 0; v < V; ++v) {
+            double* gb = reinterpret_cast<double*>(im.dst + tile_off + (size_t)v * TB);
+            if (mode & S2T_ST_STREAM) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-              __stcg(gb + (2 * c) * S2T_W + lane, cur[c][0]);
-              __stcg(gb + (2 * c + 1) * S2T_W + lane, cur[c][1]);
+              for (int c = 0; c < C; ++c) {
+                __stcs(gb + (2 * c) * S2T_W + lane, cur[v][c][0]);
+                __stcs(gb + (2 * c + 1) * S2T_W + lane, cur[v][c][1]);
+              }
+              __stcs(reinterpret_cast<int*>(gb + 2 * C * S2T_W) + lane, cur_e[v]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < C; ++c) {
+                __stcg(gb + (2 * c) * S2T_W + lane, cur[v][c][0]);
+                __stcg(gb + (2 * c + 1) * S2T_W + lane, cur[v][c][1]);
+              }
+              __stcg(reinterpret_cast<int*>(gb + 2 * C * S2T_W) + lane, cur_e[v]);
             }
-            __stcg(reinterpret_cast<int*>(gb + 2 * C * S2T_W) + lane, cur_e);
           }
         }
         if (mode & (S2T_ST_SMEM | S2T_ST_BULK)) {
@@ -505,17 +546,21 @@ __global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const Laun
             if (mode & S2T_ST_SMEM) s2t_bulk_wait_read<0>(); else s2t_bulk_wait_read<1>();
             __syncwarp();
           }
-          double* sb = reinterpret_cast<double*>(mybufs + (size_t)im.out_buf * TB);
+          unsigned char* sb0 = mybufs + (size_t)im.out_buf * V * TB;
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            sb[(2 * c) * S2T_W + lane] = cur[c][0];
-            sb[(2 * c + 1) * S2T_W + lane] = cur[c][1];
+          for (int v = 0; v < V; ++v) {
+            double* sb = reinterpret_cast<double*>(sb0 + (size_t)v * TB);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              sb[(2 * c) * S2T_W + lane] = cur[v][c][0];
+              sb[(2 * c + 1) * S2T_W + lane] = cur[v][c][1];
+            }
+            reinterpret_cast<int*>(sb + 2 * C * S2T_W)[lane] = cur_e[v];
           }
-          reinterpret_cast<int*>(sb + 2 * C * S2T_W)[lane] = cur_e;
           if (mode & S2T_ST_BULK) {
             s2t_fence_async_smem();
             __syncwarp();
-            if (lane == 0) s2t_bulk_s2g(im.dst + tile_off, sb, TB);
+            if (lane == 0) s2t_bulk_s2g(im.dst + tile_off, sb0, V * TB);
             groups_pending = true;
           }  // (a pushed tile is popped by the lanes that wrote it: columns are lane-private, no barrier needed)
         }
@@ -533,7 +578,7 @@ __global__ void __launch_bounds__(S2T_THREADS, MINB) prune_s2t_kernel(const Laun
             const int kind = dn->kind[ch];
             const void* row = kind == SRC_TIP ? (t == 0 ? dn->src[ch] : nullptr) : (kind == SRC_CHERRY ? dn->ctip[ch][t] : nullptr);
             if (row != nullptr) {
-              const char* a = static_cast<const char*>(row) + (tile - warp) * S2T_W;   // the block's 256 sites
+              const char* a = static_cast<const char*>(row) + (int64_t)blockIdx.x * S2T_WARPS * S2T_W;   // the block's 256 sites
               asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
               asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
             }

@@ -572,17 +572,20 @@ def test_c1_at_its_stated_length_unmodified_script(gpu_backend, tmp_path, monkey
     assert sorted(counters) == sorted(meta["counters"])
 
 
-@pytest.mark.parametrize("n_taxa,n_sites,model,slots,n_cats,minb,bulk",
-                         [(2, 70, "F81", 3, 4, 2, 0), (12, 333, "F81", 3, 4, 3, 0), (40, 1000, "GTR", 1, 4, 2, 1),
-                          (64, 3000, "GTR", 0, 4, 3, 0), (33, 257, "F81", 2, 4, 2, 0), (200, 640, "GTR", 4, 4, 2, 0),
-                          (200, 640, "GTR", 3, 4, 3, 1), (25, 500, "F81", 3, 1, 2, 0), (90, 2100, "GTR", 2, 1, 3, 1)])
-def test_tiled_two_state_kernel_small_inputs(n_taxa, n_sites, model, slots, n_cats, minb, bulk, gpu_backend, monkeypatch):
+@pytest.mark.parametrize("n_taxa,n_sites,model,slots,n_cats,minb,bulk,v",
+                         [(2, 70, "F81", 3, 4, 2, 0, 2), (12, 333, "F81", 3, 4, 3, 0, 1), (40, 1000, "GTR", 1, 4, 2, 1, 1),
+                          (64, 3000, "GTR", 0, 4, 3, 0, 1), (33, 257, "F81", 2, 4, 2, 0, 2), (200, 640, "GTR", 4, 4, 2, 0, 2),
+                          (200, 640, "GTR", 3, 4, 3, 1, 1), (25, 500, "F81", 3, 1, 2, 0, 2), (90, 2100, "GTR", 2, 1, 3, 1, 1),
+                          (64, 3000, "GTR", 1, 4, 2, 1, 2), (150, 900, "F81", 4, 4, 2, 0, 1), (120, 1500, "GTR", 2, 4, 4, 0, 1),
+                          (120, 1500, "F81", 3, 4, 3, 0, 2), (30, 400, "GTR", 2, 1, 4, 0, 1)])
+def test_tiled_two_state_kernel_small_inputs(n_taxa, n_sites, model, slots, n_cats, minb, bulk, v, gpu_backend, monkeypatch):
     """The large-alignment 2-state kernel (kernels_s2t.cuh: tile-interleaved partials, shared-memory stack, op images,
     cp.async code ring) forced onto small inputs: ragged last blocks, 0-4 stack slots (spills through global memory),
     both occupancy variants, plain and bulk-async stores, every schedule, dirty paths and batches -- and bit-identical
     partials to the row-major kernel."""
     monkeypatch.setenv("CYBAYES_S2T_MINB", str(minb))
     monkeypatch.setenv("CYBAYES_S2T_BULK", str(bulk))
+    monkeypatch.setenv("CYBAYES_S2T_V", str(v))     # tiles per warp
     from cybayes_b200.engine import Engine
     from cybayes_b200.likelihood import _Plan
     monkeypatch.setenv("CYBAYES_S2_TILED", "1")
