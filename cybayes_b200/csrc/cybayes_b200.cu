@@ -1207,7 +1207,7 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
         if (n_lists == 1) {
           const int64_t tile_sites = c->s2_tiled ? S2T_THREADS : (c->family_s2 ? (int64_t)256 * c->s2_vec : (c->dmma_rc ? RC_T : (c->use_dmma ? DM_T : GEN_T)));
           const int64_t blocks = (c->P + tile_sites - 1) / tile_sites * (c->family_s2 ? 1 : c->n_cats);
-          const int64_t slots = (int64_t)c->sm_count * (c->s2_tiled ? 2 : (c->family_s2 ? (c->s2_vec == 1 ? 3 : 2) : (c->dmma_rc ? 1 : 2)));
+          const int64_t slots = (int64_t)c->sm_count * (c->s2_tiled ? c->s2t_minb : (c->family_s2 ? (c->s2_vec == 1 ? 3 : 2) : (c->dmma_rc ? 1 : 2)));
           if (blocks < 4 * slots && n >= 64 && !(flags & CB_EVAL_FORCE_WALK))
             limit = std::max(16, std::min(256, (int)(n * blocks / (8 * slots)) + 1));
           if (plan.split_env > 0) limit = std::max(2, plan.split_env);

@@ -194,16 +194,8 @@ __global__ void __launch_bounds__(32) s2t_image_kernel(const LaunchConst k, int 
     const int kind = op->kind[ch];
     if (kind == SRC_CHERRY) continue;
     const double2 pr = __ldg(reinterpret_cast<const double2*>(s2_pmat(k, op->pslot[ch][c])) + i);
-    double* base = &im->tab[ch][0];
-    if (kind == SRC_TIP) {
-      double* q = base + (c * 2 + i) * 4;
-      q[0] = pr.x;
-      q[1] = pr.y;
-      q[2] = s2_tip_term(pr, 2);
-      q[3] = 0.0;
-    } else {
-      reinterpret_cast<double2*>(base)[c * 2 + i] = pr;
-    }
+    reinterpret_cast<double2*>(&im->tab[ch][0])[c * 2 + i] = pr;   // tips use the same rows (see s2t_child)
+    (void)kind;
   }
   // lookup tables of folded cherries (one thread per child and pair of tip codes)
   for (int idx = t; idx < 18; idx += 32) {
@@ -309,20 +301,32 @@ __device__ __forceinline__ void s2t_child(const S2TImage& im, const double (&cur
 #pragma unroll
     for (int v = 0; v < V; ++v) { if (FIRST) e_in[v] = se[v]; else e_in[v] += se[v]; }
   } else if constexpr (KIND == SRC_TIP) {
-    // state code 0 / 1 / 2 ('?', '-', '0/1') selects the staged contribution of this edge
+    // A tip is its 0/1 indicator column (utils.pyx:99-111): state code 0 -> (1, 0), 1 -> (0, 1), missing -> (1, 1), run
+    // through the same FMA chain as an internal child -- P[i][0], P[i][1] or fma(P[i][1], 1, P[i][0]) bit for bit.  The
+    // P rows are broadcast loads shared by the V sites: 8 shared-memory wavefronts instead of 16 per site for a
+    // per-lane table look-up (the kernel is bound by the shared-memory data pipe, not by FP64 issue).
+    double m0[V], m1[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const double* row = pbase + min((unsigned)codes[(2 * CH) * (S2T_W * V) + v * S2T_W + lane], 2u);
+      const unsigned cd = codes[(2 * CH) * (S2T_W * V) + v * S2T_W + lane];
+      m0[v] = cd == 1u ? 0.0 : 1.0;
+      m1[v] = cd == 0u ? 0.0 : 1.0;
+    }
+    const double2* pm = reinterpret_cast<const double2*>(pbase);
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
+    for (int c = 0; c < C; ++c) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const double x = row[(c * 2 + i) * 4];
+      for (int i = 0; i < 2; ++i) {
+        const double2 pr = pm[c * 2 + i];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const double x = fma(pr.y, m1[v], pr.x * m0[v]);
           if (FIRST) acc[v][c][i] = x; else acc[v][c][i] *= x;
         }
       }
-      if (FIRST) e_in[v] = 0;
     }
+#pragma unroll
+    for (int v = 0; v < V; ++v) if (FIRST) e_in[v] = 0;
   } else {  // folded cherry: the pair of tip codes selects a precomputed row
 #pragma unroll
     for (int v = 0; v < V; ++v) {
