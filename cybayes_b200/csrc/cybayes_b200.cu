@@ -1208,7 +1208,10 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
           const int64_t tile_sites = c->s2_tiled ? S2T_THREADS : (c->family_s2 ? (int64_t)256 * c->s2_vec : (c->dmma_rc ? RC_T : (c->use_dmma ? DM_T : GEN_T)));
           const int64_t blocks = (c->P + tile_sites - 1) / tile_sites * (c->family_s2 ? 1 : c->n_cats);
           const int64_t slots = (int64_t)c->sm_count * (c->s2_tiled ? c->s2t_minb : (c->family_s2 ? (c->s2_vec == 1 ? 3 : 2) : (c->dmma_rc ? 1 : 2)));
-          if (blocks < 4 * slots && n >= 64 && !(flags & CB_EVAL_FORCE_WALK))
+          // (the tiled kernel's blocks walk the whole list -- 0.7 ms each on C4 -- so even at 9 waves the ragged last wave
+          // costs 2-3 %, and 12 % at 4.4 waves: it splits up to 16 waves, measured 6.07 -> 5.91 ms on 1 GPU and 3.28 -> 2.98 ms
+          // per GPU on 2)
+          if (blocks < (c->s2_tiled ? 16 : 4) * slots && n >= 64 && !(flags & CB_EVAL_FORCE_WALK))
             limit = std::max(16, std::min(256, (int)(n * blocks / (8 * slots)) + 1));
           if (plan.split_env > 0) limit = std::max(2, plan.split_env);
           if (limit >= n) limit = n + 1;  // nothing to cut
@@ -1254,6 +1257,13 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
               const bool a_first = ca < cb2 || (ca == cb2 && n_sub[a] >= n_sub[b2]);
               fj = a_first ? ca : cb2;
               first_kid[(size_t)j * (K + 1) + kk] = a_first ? 0 : 1;
+              // third choice: read the first child back although a slot is free, so that the second keeps all kk slots
+              // (one read-back here instead of one at every fork of a subtree left with too few slots)
+              const int cs = f[(size_t)a * (K + 1) + kk] + 1 + f[(size_t)b2 * (K + 1) + kk];
+              if (kk > 0 && cs < fj) {
+                fj = cs;
+                first_kid[(size_t)j * (K + 1) + kk] = (n_sub[a] >= n_sub[b2] ? 0 : 1) | 2;
+              }
             } else if (a >= 0) {
               fj = f[(size_t)a * (K + 1) + kk];
             } else if (b2 >= 0) {
@@ -1275,12 +1285,13 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
             if (b2 >= 0 && seg_of[b2] != seg_of[j]) b2 = -1;
             if (a >= 0 && b2 >= 0) {
               const int fk = first_kid[(size_t)j * (K + 1) + kk];
-              const int x = fk == 0 ? a : b2, y = fk == 0 ? b2 : a;
+              const bool push = kk > 0 && !(fk & 2);
+              const int x = (fk & 1) == 0 ? a : b2, y = (fk & 1) == 0 ? b2 : a;
               if (t.phase == 0) { t.phase = 1; fr.push_back({x, kk, 0}); continue; }
               if (t.phase == 1) {
-                push_slot[x] = kk > 0 ? slot_base + (K - kk) : -1;
+                push_slot[x] = push ? slot_base + (K - kk) : -1;
                 t.phase = 2;
-                fr.push_back({y, kk > 0 ? kk - 1 : 0, 0});
+                fr.push_back({y, push ? kk - 1 : kk, 0});
                 continue;
               }
             } else if (a >= 0 || b2 >= 0) {

@@ -189,7 +189,7 @@ def reset_engines():
 class _Plan:
     """Edge list -> node operations.  `nodes[i]` is completed by the i-th op in the order in
     which the reference finishes parents while walking `edges` (ML_gamma.pyx:24-36)."""
-    __slots__ = ("edges", "node_list", "kids", "index", "_nodes", "_children", "_edge_keys", "_paths")
+    __slots__ = ("edges", "node_list", "kids", "index", "_nodes", "_children", "_edge_keys", "_paths", "_perms")
 
     def __init__(self, edges):
         self.edges = list(edges)
@@ -208,6 +208,7 @@ class _Plan:
         self.index = dict(zip(node_list, range(len(node_list))))
         self._nodes = self._children = self._edge_keys = None
         self._paths = {}   # dirty set -> (nodes, children, edge keys, getter): the same few paths recur while a tree lives
+        self._perms = []   # (key order of a transition-matrix table, positions of this plan's edges in it), MRU
 
     @property
     def nodes(self):
@@ -230,6 +231,30 @@ class _Plan:
         return self._edge_keys
 
 
+    def perm_for(self, src):
+        """Positions of this plan's edges (op order) in `src`, the key order of a table that holds exactly these edges;
+        None when it holds other edges.  A chain hands over tables in the same key order evaluation after evaluation
+        (the order of its tree dict), so the match is one list comparison -- pointer-equal tuples mostly -- instead of
+        one dict lookup per edge and category."""
+        perms = self._perms
+        for i, (keys, perm) in enumerate(perms):
+            if keys is src or keys == src:
+                if i:
+                    perms.insert(0, perms.pop(i))
+                return perm
+        edge_keys = self.edge_keys
+        if len(src) != len(edge_keys):
+            return None
+        where = dict(zip(src, range(len(src))))
+        try:
+            perm = np.fromiter(map(where.__getitem__, edge_keys), dtype=np.int32, count=len(edge_keys))
+        except KeyError:
+            return None
+        perms.insert(0, (src, perm))
+        del perms[4:]
+        return perm
+
+
 _plan_cache = []  # small MRU list of plans, matched by list equality
 
 
@@ -245,48 +270,89 @@ def _plan_for(edges):
     return p
 
 
-def _gather_host_matrices(vals, n, S):
-    """(n, S, S) float64 array from n reference-style (S, S) ndarrays.  bytes.join walks the buffer protocol in C
-    (~60 ns per matrix against ~320 ns for np.concatenate) and refuses non-contiguous arrays; anything unusual
-    (other dtypes, views, nested lists) takes the general route."""
-    try:
-        if vals[0].dtype == np.float64 and vals[-1].dtype == np.float64:
-            buf = b"".join(vals)
-            if len(buf) == n * S * S * 8:
-                return np.frombuffer(buf, dtype=np.float64)
-    except (AttributeError, TypeError, BufferError, ValueError):
-        pass
+try:   # optional CPython helper (csrc/hostgather.c): same bytes as the bytes.join route below, ~10x faster
+    from . import _hostgather
+except ImportError:   # not built: host-side glue only, the join route gives identical arrays
+    _hostgather = None
+
+
+def _gather_host_matrices(vals, n, S, out=None):
+    """(n * S * S,) float64 array (`out` when given) from n reference-style (S, S) ndarrays.  The packed copy goes
+    through _hostgather.pack (reads the array structs, ~10 ns per matrix) or, when that module is not built,
+    bytes.join (buffer protocol, ~100 ns per matrix; np.concatenate needs ~320 ns); both refuse anything but
+    contiguous float64 arrays, which then take the general route (other dtypes, views, nested lists)."""
+    if out is None:
+        out = np.empty(n * S * S, dtype=np.float64)
+    if _hostgather is not None:
+        if _hostgather.pack(vals, out):
+            return out
+    else:
+        try:
+            if vals[0].dtype == np.float64 and vals[-1].dtype == np.float64:
+                buf = b"".join(vals)
+                if len(buf) == n * S * S * 8:
+                    out[:] = np.frombuffer(buf, dtype=np.float64)
+                    return out
+        except (AttributeError, TypeError, BufferError, ValueError):
+            pass
     mats = np.array([np.asarray(v, dtype=np.float64) for v in vals])
     if mats.shape != (n, S, S):
         raise ValueError(f"transition matrices must be {S} x {S}")
-    return mats
+    out[:] = mats.ravel()
+    return out
 
 
-def _slot_matrix(engine, tmats, edge_keys, getter=None):
+def _slot_matrix(engine, tmats, edge_keys, getter=None, plan=None):
     """(n_edges, C) int32 P-slot table for the ops' edges.  Device tables are looked up; reference-style host dicts
-    of ndarrays are gathered in op order and uploaded with ONE host -> device copy for all categories."""
+    of ndarrays are gathered and uploaded with ONE host -> device copy for all categories.  With `plan` (full
+    evaluations) a table that holds exactly the plan's edges is taken in its own key order and mapped onto the op
+    order by the plan's cached permutation; anything else goes edge by edge through `getter`."""
     cols = []
-    if getter is None:
-        getter = itemgetter(*edge_keys) if len(edge_keys) > 1 else (lambda d: (d[edge_keys[0]],))
     keep = []
     n = len(edge_keys)
     S = engine.n_states
-    host = []   # (column index, matrices) of the host-side categories
+    n_host = sum(1 for t in tmats if not isinstance(t, PMatTable))
+    packed = np.empty((n_host, n * S * S), dtype=np.float64) if n_host else None
+    host = []   # (column index, permutation or None) of the host-side categories, in the order of `packed`
     for t in tmats:
         if isinstance(t, PMatTable):
             if t.engine is not engine:
                 raise ValueError("transition matrices belong to a different alignment")
+            run = t.pristine() if plan is not None else None
+            perm = plan.perm_for(run[0]) if run is not None else None
+            if perm is not None:
+                cols.append(perm + np.int32(run[1]))
+                continue
+            if getter is None:
+                getter = itemgetter(*edge_keys) if n > 1 else (lambda d: (d[edge_keys[0]],))
             cols.append(getter(t._slots))
             continue
-        host.append((len(cols), _gather_host_matrices(getter(t), n, S)))
+        out = packed[len(host)]
+        perm = None
+        if plan is not None and type(t) is dict and len(t) == n:
+            if _hostgather is not None:    # a key order seen before: keys checked and values packed in one pass
+                for keys, known in plan._perms:
+                    if _hostgather.pack_dict(t, keys, out):
+                        perm = known
+                        break
+            if perm is None:
+                perm = plan.perm_for(list(t))
+                if perm is not None:
+                    _gather_host_matrices(list(t.values()), n, S, out)
+        if perm is None:
+            if getter is None:
+                getter = itemgetter(*edge_keys) if n > 1 else (lambda d: (d[edge_keys[0]],))
+            _gather_host_matrices(getter(t), n, S, out)
+        host.append((len(cols), perm))
         cols.append(None)
     if host:
-        block = engine.alloc_slots(n * len(host))
+        block = engine.alloc_slots(n * n_host)
         keep.append(block)
         slots = np.arange(block.base, block.base + block.n, dtype=np.int32)
-        engine.upload_pmats(slots, host[0][1] if len(host) == 1 else np.concatenate([m.ravel() for _, m in host]))
-        for j, (col, _) in enumerate(host):
-            cols[col] = slots[j * n:(j + 1) * n]
+        engine.upload_pmats(slots, packed)
+        for j, (col, perm) in enumerate(host):
+            run = slots[j * n:(j + 1) * n]
+            cols[col] = run if perm is None else run[perm]
     return np.ascontiguousarray(np.array(cols, dtype=np.int32).T), keep
 
 
@@ -399,7 +465,7 @@ def _full(pi, root, ll_mats, edges, tmats, n_cats_tables):
     plan = _plan_for(edges)
     if plan.nodes[-1] != root:
         raise KeyError(root)
-    pslots, keep = _slot_matrix(engine, tmats, plan.edge_keys)
+    pslots, keep = _slot_matrix(engine, tmats, plan.edge_keys, plan=plan)
     nodes = plan.nodes if STORE_ROOT else plan.nodes[:-1]
     if engine.n_patterns >= LAZY_CACHE_MIN_SITES or not _cache_fits(engine, len(plan.nodes)):
         lnl, _ = engine.eval(None, plan.nodes, plan.children, pslots, np.asarray(pi, dtype=np.float64),

@@ -63,8 +63,13 @@ class PMatrix:
 
 
 class PMatTable:
-    """Mapping edge -> PMatrix over device slots (one rate category)."""
-    __slots__ = ("engine", "_slots", "_owners", "_block")
+    """Mapping edge -> PMatrix over device slots (one rate category).
+
+    A table as get_prob_t / get_prob_t_all return it is a run of consecutive slots in the order of the edge list it
+    was built from; the edge -> slot dict is only materialised when somebody indexes or edits the table (`_slots`).
+    Until then `pristine()` hands matML the (edge list, first slot) pair, and a full evaluation maps the run onto
+    its op order with one cached permutation instead of one dict lookup per edge."""
+    __slots__ = ("engine", "_map", "_owners", "_block", "_edges", "_base")
 
     def __init__(self, engine, edges, block, base=None, n=None):
         # (base, n): this table's slice of a block shared by the tables of all rate categories
@@ -72,8 +77,23 @@ class PMatTable:
         self._block = block
         if base is None:
             base, n = block.base, block.n
-        self._slots = dict(zip(edges, range(base, base + n)))
+        if len(edges) != n:
+            raise ValueError("one slot per edge")
+        self._edges, self._base = edges, base
+        self._map = None
         self._owners = {}
+
+    @property
+    def _slots(self):
+        m = self._map
+        if m is None:
+            m = self._map = dict(zip(self._edges, range(self._base, self._base + len(self._edges))))
+            self._edges = None
+        return m
+
+    def pristine(self):
+        """(edge list, first slot) while nobody has looked inside the table, else None."""
+        return (self._edges, self._base) if self._map is None else None
 
     def __getitem__(self, edge):
         return PMatrix(self.engine, self._slots[edge], self._owners.get(edge, self._block))
@@ -117,7 +137,9 @@ class PMatTable:
     def copy(self):
         t = PMatTable.__new__(PMatTable)
         t.engine, t._block = self.engine, self._block
-        t._slots, t._owners = dict(self._slots), dict(self._owners)
+        t._edges, t._base = self._edges, self._base
+        t._map = None if self._map is None else dict(self._map)
+        t._owners = dict(self._owners)
         return t
 
 

@@ -310,6 +310,65 @@ def test_get_prob_t_all_equals_per_category_calls(name, golden_cases, fake_backe
     assert base in eng._free_slots.get(n, [])
 
 
+def test_slot_tables_by_key_order_equal_slot_tables_by_lookup(golden_cases, fake_backend):
+    """Full evaluations map a transition-matrix table onto the op order with one permutation per key order instead
+    of one lookup per edge: device tables as built, host dicts in any insertion order, edited tables and dicts with
+    foreign keys (which fall back to the lookups) must all give the per-edge result."""
+    import random as pyrandom
+    from cybayes_b200 import config, likelihood
+    from cybayes_b200.driver import load_alignment
+    from cybayes_b200.ML_gamma import matML
+    from cybayes_b200.subst import get_edge_transition_mat, get_prob_t, get_prob_t_all
+    case = golden_cases["narrow_F81"]
+    load_alignment(golden_io.data_path(case), case["dtype"], case["reader"])
+    config.MODEL, config.NORM_BETA = case["model"], case["norm_beta"]
+    tree, pi, rates, edges, site_rates = golden_io.case_state(case)
+    args = (config.N_SITES, config.N_TAXA, config.N_CATS)
+    want = golden_io.oracle_lnl(case)
+    plan = likelihood._plan_for(edges)
+    eng, _ = likelihood.engine_for(config.LEAF_LLMAT, config.N_CATS)
+
+    def by_lookup(tables):
+        got, keep = likelihood._slot_matrix(eng, tables, plan.edge_keys)
+        return got, keep
+
+    tabs = get_prob_t_all(pi, tree, rates, site_rates)
+    assert all(t.pristine() is not None for t in tabs)
+    fast, _ = likelihood._slot_matrix(eng, tabs, plan.edge_keys, plan=plan)
+    assert all(t.pristine() is not None for t in tabs)          # no dict was built on the way
+    slow, _ = by_lookup(tabs)
+    assert np.array_equal(fast, slow) and len(plan._perms) == 1
+    lnl, _ = matML(pi, case["root"], config.LEAF_LLMAT, edges, tabs, *args)
+    assert abs(lnl - want) <= 1e-11 * abs(want)
+    # host dicts, shuffled insertion order, one order per category
+    rng = pyrandom.Random(5)
+    host = []
+    for t in [get_prob_t(pi, tree, rates, r) for r in site_rates]:
+        keys = list(tree)
+        rng.shuffle(keys)
+        host.append({e: np.array(t[e]) for e in keys})
+    lnl, _ = matML(pi, case["root"], config.LEAF_LLMAT, edges, host, *args)
+    assert abs(lnl - want) <= 1e-11 * abs(want)
+    fast, keep1 = likelihood._slot_matrix(eng, host, plan.edge_keys, plan=plan)
+    slow, keep2 = by_lookup(host)
+    assert np.array_equal(eng.download_pmats(fast.T.ravel()), eng.download_pmats(slow.T.ravel()))
+    # an edited table and a dict with a key the plan does not have take the per-edge route
+    e = list(tree)[3]
+    tabs[1][e] = get_edge_transition_mat(pi, rates, tree[e] * site_rates[1] * 1.5)
+    assert tabs[1].pristine() is None
+    host[2][(9999, 9998)] = np.eye(len(pi))
+    mixed = [tabs[0], tabs[1], host[2], host[3]]
+    fast, keep3 = likelihood._slot_matrix(eng, mixed, plan.edge_keys, plan=plan)
+    slow, keep4 = by_lookup(mixed)
+    assert np.array_equal(eng.download_pmats(fast.T.ravel()), eng.download_pmats(slow.T.ravel()))
+    assert np.array_equal(fast[:, :2], slow[:, :2])
+    bad = dict(host[3])
+    del bad[e]
+    bad[(9999, 9998)] = np.eye(len(pi))                           # right size, wrong edges
+    with pytest.raises(KeyError):
+        likelihood._slot_matrix(eng, [bad], plan.edge_keys, plan=plan)
+
+
 def test_dirty_path_op_lists_are_cached_per_plan(golden_cases, fake_backend):
     """cache_matML keeps the op list of a dirty path with its plan: repeated branch moves on one edge reuse it, and the
     cached and the first evaluation agree."""
