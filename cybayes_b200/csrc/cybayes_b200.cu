@@ -1208,10 +1208,10 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
           const int64_t tile_sites = c->s2_tiled ? S2T_THREADS : (c->family_s2 ? (int64_t)256 * c->s2_vec : (c->dmma_rc ? RC_T : (c->use_dmma ? DM_T : GEN_T)));
           const int64_t blocks = (c->P + tile_sites - 1) / tile_sites * (c->family_s2 ? 1 : c->n_cats);
           const int64_t slots = (int64_t)c->sm_count * (c->s2_tiled ? c->s2t_minb : (c->family_s2 ? (c->s2_vec == 1 ? 3 : 2) : (c->dmma_rc ? 1 : 2)));
-          // (the tiled kernel's blocks walk the whole list -- 0.7 ms each on C4 -- so even at 9 waves the ragged last wave
-          // costs 2-3 %, and 12 % at 4.4 waves: it splits up to 16 waves, measured 6.07 -> 5.91 ms on 1 GPU and 3.28 -> 2.98 ms
-          // per GPU on 2)
-          if (blocks < (c->s2_tiled ? 16 : 4) * slots && n >= 64 && !(flags & CB_EVAL_FORCE_WALK))
+          // Every block walks the whole list (0.7 ms on C4, 3 ms on a C5 shard), so a ragged last wave is expensive even
+          // at many waves: 2-3 % at 8.8 waves, 12 % at 4.4 and 5.3.  Measured: C4 6.07 -> 5.91 ms on 1 GPU and 3.28 ->
+          // 2.98 ms per GPU on 2; the C5 shard of an 8-GPU run (25 000 patterns x 64 states) 17.7 -> 15.9 ms.
+          if (blocks < 16 * slots && n >= 64 && !(flags & CB_EVAL_FORCE_WALK))
             limit = std::max(16, std::min(256, (int)(n * blocks / (8 * slots)) + 1));
           if (plan.split_env > 0) limit = std::max(2, plan.split_env);
           if (limit >= n) limit = n + 1;  // nothing to cut
