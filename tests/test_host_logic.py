@@ -400,3 +400,53 @@ def test_large_shape_parity_bodies_dry_run(fake_backend, monkeypatch):
     large_cases.run_c4_shape(48, 512, 128)
     likelihood.reset_engines()
     large_cases.run_c5_shape(12, 256, 64, 128)
+
+
+def test_hostgather_packs_like_bytes_join(tmp_path):
+    """csrc/hostgather.c (optional CPython helper of the host-table route): same bytes as the bytes.join route, and a
+    clean False -- never a partial success -- on anything that is not a plain float64 matrix or the expected key order."""
+    import subprocess
+    from cybayes_b200 import likelihood
+    hg = likelihood._hostgather
+    if hg is None:
+        csrc = os.path.join(os.path.dirname(os.path.abspath(likelihood.__file__)), "csrc")
+        if subprocess.run(["make", "-C", csrc, "../_hostgather.so"], capture_output=True).returncode != 0:
+            pytest.skip("_hostgather cannot be built here")
+        from cybayes_b200 import _hostgather as hg
+    rng = np.random.default_rng(3)
+    mats = [rng.random((3, 3)) for _ in range(50)]
+    out = np.empty(50 * 9)
+    assert hg.pack(mats, out) is True and out.tobytes() == b"".join(mats)
+    assert hg.pack(tuple(mats), out) is True
+    assert hg.pack([], np.empty(0)) is True
+    for bad in (mats[0].T, mats[0].astype(np.float32), mats[0].tolist(), rng.random((3, 4)), mats[0][:, ::-1],
+                mats[0].astype(">f8")):
+        assert hg.pack(mats[:10] + [bad] + mats[11:], out) is False
+    with pytest.raises(TypeError):
+        hg.pack(mats, np.empty(50 * 9, dtype=np.float32))
+    with pytest.raises(TypeError):
+        hg.pack(mats, np.empty((50, 18))[:, ::2])
+    keys = [(i, i + 100) for i in range(50)]
+    table = dict(zip(keys, mats))
+    out2 = np.empty(50 * 9)
+    assert hg.pack_dict(table, keys, out2) is True and out2.tobytes() == out.tobytes()
+    assert hg.pack_dict(table, [(int(a), int(b)) for a, b in keys], out2) is True          # equal, not identical, keys
+    assert hg.pack_dict(table, keys[::-1], out2) is False                                    # other order
+    assert hg.pack_dict(table, keys[:-1], out2) is False and hg.pack_dict(table, keys + [(1, 1)], out2) is False
+    assert hg.pack_dict(dict(table, **{}), keys, np.empty(50 * 9 + 1)) is False              # size does not divide
+    table[keys[7]] = mats[7].T
+    assert hg.pack_dict(table, keys, out2) is False
+    import collections
+    assert hg.pack_dict(collections.OrderedDict(zip(keys, mats)), keys, out2) is False       # exact dicts only
+    # the gather used by matML gives the same array with and without the module
+    want = likelihood._gather_host_matrices(mats, 50, 3).copy()
+    saved = likelihood._hostgather
+    try:
+        likelihood._hostgather = None
+        assert np.array_equal(likelihood._gather_host_matrices(mats, 50, 3), want)
+        likelihood._hostgather = hg
+        assert np.array_equal(likelihood._gather_host_matrices(mats, 50, 3), want)
+        odd = [m.astype(np.float32) for m in mats]                                           # general route
+        assert np.allclose(likelihood._gather_host_matrices(odd, 50, 3), want, rtol=1e-6)
+    finally:
+        likelihood._hostgather = saved
