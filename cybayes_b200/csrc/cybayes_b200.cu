@@ -1211,8 +1211,15 @@ static int build_plan(cb_ctx* c, const Snapshot* sin, int n_lists, const int32_t
           // Every block walks the whole list (0.7 ms on C4, 3 ms on a C5 shard), so a ragged last wave is expensive even
           // at many waves: 2-3 % at 8.8 waves, 12 % at 4.4 and 5.3.  Measured: C4 6.07 -> 5.91 ms on 1 GPU and 3.28 ->
           // 2.98 ms per GPU on 2; the C5 shard of an 8-GPU run (25 000 patterns x 64 states) 17.7 -> 15.9 ms.
-          if (blocks < 16 * slots && n >= 64 && !(flags & CB_EVAL_FORCE_WALK))
-            limit = std::max(16, std::min(256, (int)(n * blocks / (8 * slots)) + 1));
+          // Under one wave the cut is there for parallelism (about 8 waves of ranges); from one wave up it only has to
+          // even out the tail, and a small limit costs more in the launch of the ops above the cut (16 ops at limit 93
+          // on a 125 000-pattern shard: 65 us of 800) than it gains: a third of the tree per range measured best there
+          // (0.794 -> 0.77 ms).
+          if (blocks < 16 * slots && n >= 64 && !(flags & CB_EVAL_FORCE_WALK)) {
+            int lim = (int)(n * blocks / (8 * slots)) + 1;
+            if (blocks >= slots) lim = std::max(lim, n / 3);
+            limit = std::max(16, std::min(256, lim));
+          }
           if (plan.split_env > 0) limit = std::max(2, plan.split_env);
           if (limit >= n) limit = n + 1;  // nothing to cut
         }
