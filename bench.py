@@ -85,34 +85,99 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+_NVML_SAMPLER = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+out = open(sys.argv[2], "w")
+print("ready", mx, file=out, flush=True)
+while True:
+    t = time.time()
+    print(t, nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(reasons(h)), file=out, flush=True)
+    time.sleep(0.005)
+"""
+
+
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU while the timed region runs.  A helper process polls NVML every few
+    milliseconds with wall-clock stamps (the timed region of a sharded run is only tens of milliseconds long: a
+    100 ms `nvidia-smi -lms` loop can miss it entirely); it is started before the warm-up steps, `begin()` / `stop()`
+    bracket the timed region and only the samples in between are reported.  Without pynvml: `nvidia-smi -lms`."""
+    SMI_FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # NVML reason bits (nvml.h): SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, device):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.tmp.close()
+        self.t_begin = self.t_end = None
+        self.mode, self.proc = "nvml", None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
-                                         stderr=subprocess.DEVNULL)
+            import pynvml  # noqa: F401  (only to choose the sampler; the polling happens in the helper process)
+            self.proc = subprocess.Popen([sys.executable, "-c", _NVML_SAMPLER, str(device), self.tmp.name],
+                                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            for _ in range(400):   # wait until the helper has initialised NVML (first line of its file)
+                if os.path.getsize(self.tmp.name) > 0 or self.proc.poll() is not None:
+                    break
+                time.sleep(0.005)
+            if self.proc.poll() is not None or os.path.getsize(self.tmp.name) == 0:
+                raise RuntimeError("NVML sampler did not start")
         except Exception:
-            self.proc = None
+            self._kill()
+            self.mode = "smi"
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.SMI_FIELDS}",
+                                              "--format=csv,noheader,nounits", "-lms", "20"],
+                                             stdout=open(self.tmp.name, "w"), stderr=subprocess.DEVNULL)
+            except Exception:
+                self.proc = None
+
+    def _kill(self):
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.terminate()
+            self.proc.wait()
+
+    def begin(self):
+        self.t_begin = time.time()
 
     def stop(self):
+        self.t_end = time.time()
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.proc.wait()
-        self.tmp.flush()
-        rows = [l.strip().split(", ") for l in open(self.tmp.name) if l.strip()]
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock sampler available"], "samples": 0}
+        time.sleep(0.15)   # the power-cap flag lags the load by tens of milliseconds: keep polling a little longer
+        self._kill()
+        lines = [l.split() if self.mode == "nvml" else l.strip().split(", ") for l in open(self.tmp.name) if l.strip()]
         os.unlink(self.tmp.name)
-        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].strip() == "Active"})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.mode == "smi":
+            sm = [float(r[0]) for r in lines if r[0].replace(".", "").isdigit()]
+            mx = [float(r[1]) for r in lines if r[1].replace(".", "").isdigit()]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = sorted({names[i] for r in lines if len(r) >= 6 for i in range(4) if r[2 + i].strip() == "Active"})
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                    "reasons": reasons, "samples": len(sm), "sampler": "nvidia-smi -lms 20 (whole run incl. warm-up)"}
+        mx = float(lines[0][1]) if lines and lines[0][0] == "ready" else None
+        rows = [(float(r[0]), float(r[1]), int(r[2])) for r in lines[1:] if len(r) == 3]
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        inside = [r for r in rows if t0 <= r[0] <= self.t_end]
+        scope = "timed region"
+        if not inside:   # a region shorter than one polling period: the samples just around it
+            inside = [r for r in rows if t0 - 0.02 <= r[0] <= self.t_end + 0.005]
+            scope = "timed region +- 20 ms"
+        mask = run_mask = 0
+        for r in inside:
+            mask |= r[2]
+        for r in rows:
+            run_mask |= r[2]
+        names = lambda m: sorted(k for k, bit in self.BITS.items() if m & bit)  # noqa: E731
+        return {"sm_mhz": statistics.median([r[1] for r in inside]) if inside else None, "sm_max_mhz": mx,
+                "reasons": names(mask | run_mask), "reasons_in_timed_region": names(mask), "samples": len(inside),
+                "samples_whole_run": len(rows), "sm_mhz_min": min((r[1] for r in inside), default=None),
+                "sampler": f"NVML every 5 ms; clocks: {scope}; reasons: warm-up to 150 ms after the timed region (the "
+                           "power-cap flag lags the load)"}
 
 
 def host_cores():
@@ -377,11 +442,13 @@ def run_c4(a):
         if dist is not None:
             dist.barrier()
 
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(a.warmup):
         lnl = step()
     barrier()
     eng.sync()
-    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.begin()
     st0 = eng.stats()
     kernel_ms, main_ms = [], []
     eng.host_profile()
@@ -494,6 +561,14 @@ def run_c4(a):
         "data_generation_s": t_gen,
     }
 
+    if not a.no_extras:
+        # MCMC generations/s on THIS alignment (all ranks: every evaluation of a sharded chain is collective): the
+        # generation loop inside the library (cb_chain_*), GTR + Gamma-4 moves of mat_mcmc_gamma.py:65-84
+        try:
+            out["mcmc_on_workload"] = mcmc_on_workload(eng, aln, pi, dist, n_gen=max(40, min(400, 20 * a.steps)))
+        except Exception as exc:  # extras must never sink the headline number
+            out["mcmc_on_workload"] = {"error": repr(exc)}
+
     if rank == 0 and world == 1 and not a.no_extras:
         # dirty-path evaluations (cache_matML's job) on the same alignment: random tip -> root paths
         l_full, snap = eng.eval(None, plan.nodes, plan.children, pslots, pi, want_snapshot=True)
@@ -568,11 +643,18 @@ def run_c4(a):
             likelihood.reset_engines()
             os.environ["CYBAYES_COMPRESS_MAX_SITES"] = "250000"
             likelihood.COMPRESS_MAX_SITES = 250000
+            from cybayes_b200.fastchain import run_chain_native
             res = run_chain(os.path.join(DATA, "narrow.phy"), "F81", 3000, 1000, "bin",
                             os.path.join(tempfile.gettempdir(), "bench_narrow"), out=io.StringIO())
-            out["mcmc"] = {"gens_per_sec": res["gens_per_sec"], "config": "C1 narrow.phy F81 bin Gamma-4, 3000 "
-                           "generations through cybayes_b200.driver (same trace as the reference driver)",
-                           "final_lnL": float(res["state"]["logLikehood"])}
+            likelihood.reset_engines()
+            nat = run_chain_native(os.path.join(DATA, "narrow.phy"), "F81", 10000, 1000, "bin",
+                                   os.path.join(tempfile.gettempdir(), "bench_narrow_native"), out=io.StringIO())
+            out["mcmc"] = {"gens_per_sec": nat["gens_per_sec"], "driver_py_gens_per_sec": res["gens_per_sec"],
+                           "config": "C1 narrow.phy F81 bin Gamma-4: 10 000 generations with the loop inside the library "
+                                     "(cb_chain_run), 3 000 through cybayes_b200.driver (Python loop); both take the "
+                                     "reference driver's decisions generation by generation (tests)",
+                           "final_lnL": float(nat["state"]["logLikehood"]),
+                           "driver_py_final_lnL": float(res["state"]["logLikehood"])}
         except Exception as exc:  # extras must never sink the headline number
             out["mcmc"] = {"error": repr(exc)}
     elif rank == 0:
@@ -587,6 +669,50 @@ def run_c4(a):
 
 
 # ------------------------------------------------------------------------------------------------- C5
+def mcmc_on_workload(eng, aln, pi, dist, n_gen, seed=1234):
+    """n_gen Metropolis-Hastings generations on the bench alignment with the generation loop inside the library
+    (fastchain.NativeChain over the engine's own context).  Sharded runs: every rank runs the same chain (same seeds,
+    and the cross-GPU sum gives every rank the same bits), so the decisions agree without any further exchange.
+    The binary GTR model has a single exchangeability: its `rates` block is left out (the reference would
+    crash proposing it)."""
+    import random
+    from cybayes_b200 import config
+    from cybayes_b200.fastchain import MOVES, NativeChain
+    from cybayes_b200.ML_gamma import matML
+    from cybayes_b200.subst import get_prob_t_all
+    random.seed(seed)
+    np.random.seed(seed)
+    state = {"tree": dict(aln.tree), "pi": np.array(pi, dtype=np.float64), "rates": np.array(aln.er, dtype=np.float64),
+             "srates": float(aln.alpha), "root": aln.root}
+    chain = NativeChain(eng, state, list(aln.rates), "GTR", True, skip_degenerate_rates=True)
+    chain.take_rng()
+    chain.run(min(20, n_gen))                     # warm-up: plan cache, buffer pool
+    if dist is not None:
+        dist.barrier()
+    eng.sync()
+    t0 = time.perf_counter()
+    mv, acc, cur, prop, ratio, logu = chain.run(n_gen)
+    secs = _max_over_ranks(dist, time.perf_counter() - t0)
+    st = chain.state()
+    counts = {MOVES[m][1] + ":" + MOVES[m][0]: [int((mv == m).sum()), int(acc[mv == m].sum())] for m in np.unique(mv)}
+    chain.give_rng()
+    chain.close()
+    # the chain's likelihood of its final state against a fresh full evaluation of that state
+    tabs = get_prob_t_all(st["pi"], st["tree"], st["rates"], st["site_rates"])
+    from cybayes_b200.tree import adjlist2nodes_dict, postorder
+    edges = postorder(adjlist2nodes_dict(st["tree"]), aln.root)[::-1]
+    fresh, cache = matML(st["pi"], aln.root, config.LEAF_LLMAT, edges, tabs, config.N_SITES, config.N_TAXA, len(tabs))
+    del cache, tabs
+    rel = abs(float(fresh) - float(st["logLikehood"])) / abs(float(fresh))
+    assert rel <= 1e-9, (fresh, st["logLikehood"])
+    return {"gens_per_sec": n_gen / secs, "generations": n_gen, "ms_per_generation": 1e3 * secs / n_gen,
+            "moves_proposed_accepted": counts, "final_lnL": float(st["logLikehood"]),
+            "final_lnL_vs_fresh_full_evaluation_rel": rel,
+            "note": "cb_chain_run on the bench alignment (GTR + Gamma-4 move mix of mat_mcmc_gamma.py:65-84 without the "
+                    "degenerate rates block); branch / NNI / SPR proposals are dirty-path evaluations, pi / alpha "
+                    "proposals full passes"}
+
+
 def run_c5(a):
     """C5: 512 taxa x 200 000 patterns x 64 states, GTR + Gamma-4 (FP64 tensor path, prune_dmma_rc_kernel<64>).
     On one GPU the full cache (209 GB) does not fit: the step is the likelihood-only evaluation there; sharded
@@ -628,11 +754,13 @@ def run_c5(a):
     def barrier():
         if dist is not None:
             dist.barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(a.warmup):
         lnl = step()
     barrier()
     eng.sync()
-    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.begin()
     st0 = eng.stats()
     kernel_ms, main_ms = [], []
     eng.mark(0)
