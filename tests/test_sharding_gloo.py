@@ -55,6 +55,76 @@ def test_two_rank_site_sharding(tmp_path):
     assert res.returncode == 0 and "SHARDED_OK" in res.stdout, (res.stdout[-1500:], res.stderr[-3000:])
 
 
+CHAIN_WORKER = r'''
+import os, sys, random
+import numpy as np
+import torch, torch.distributed as dist
+repo = sys.argv[1]
+sys.path[:0] = [repo, os.path.join(repo, "tests"), os.path.join(repo, "oracle")]
+from fake_engine import FakeEngine
+from cybayes_b200 import config
+from cybayes_b200.fastchain import NativeChain
+from cybayes_b200.synthetic import SyntheticAlignment, shard_bounds
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+aln = SyntheticAlignment(16, 1024, 2, 11, block_sites=256)
+
+
+class ShardedEngine(FakeEngine):
+    """This rank's slice of the patterns; eval adds the shard sums in rank order (what the fused cross-GPU sum does)."""
+    def eval(self, *args, **kw):
+        part, snap = super().eval(*args, **kw)
+        parts = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, torch.tensor([part], dtype=torch.float64))
+        total = 0.0
+        for p in parts:
+            total += float(p[0])
+        return total, snap
+
+
+def run(engine, n):
+    random.seed(77); np.random.seed(77)
+    config.N_TAXA, config.N_CHARS, config.MODEL, config.IN_DTYPE, config.N_CATS = 16, 2, "GTR", "bin", 4
+    state = {"tree": dict(aln.tree), "pi": aln.pi.copy(), "rates": aln.er.copy(), "srates": float(aln.alpha), "root": aln.root}
+    chain = NativeChain(engine, state, list(aln.rates), "GTR", True, use_callbacks=True, skip_degenerate_rates=True)
+    chain.take_rng()
+    out = chain.run(n)
+    st = chain.state()
+    chain.close()
+    return out, st
+
+lo, hi = shard_bounds(aln.n_sites, rank, world, 256)
+(mv, acc, cur, prop, ratio, logu), st = run(ShardedEngine(aln.codes(lo, hi), 2, 4), 150)
+# every rank took the same moves and decisions and ends in the same state ...
+digest = torch.tensor([float(mv.sum()), float(acc.sum()), float(cur[-1]), float(st["logLikehood"]), sum(st["tree"].values())],
+                      dtype=torch.float64)
+every = [torch.zeros_like(digest) for _ in range(world)]
+dist.all_gather(every, digest)
+assert all(torch.equal(e, every[0]) for e in every), every
+if rank == 0:
+    # ... which is the chain of one rank holding the whole alignment (sums of shard sums differ from the sum over all
+    # sites in the last bits: decisions must agree, likelihoods to 1e-12)
+    (mv1, acc1, cur1, prop1, _, _), st1 = run(FakeEngine(aln.codes(0, aln.n_sites), 2, 4), 150)
+    assert np.array_equal(mv, mv1) and np.array_equal(acc, acc1) and acc.sum() > 5
+    assert np.allclose(cur, cur1, rtol=1e-12, atol=0) and np.allclose(prop, prop1, rtol=1e-12, atol=0)
+    assert list(st["tree"]) == list(st1["tree"])
+    print("SHARDED_CHAIN_OK", int(acc.sum()), float(st["logLikehood"]))
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_sharded_native_chain(tmp_path):
+    """The generation loop of the library on two ranks, each holding half of the patterns (bench.py's
+    mcmc_on_workload under torchrun): same moves, decisions and final state on both ranks and as on one rank."""
+    script = tmp_path / "chain_worker.py"
+    script.write_text(CHAIN_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", OMP_NUM_THREADS="1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613", str(script), REPO],
+                         capture_output=True, text=True, env=env, timeout=900)
+    assert res.returncode == 0 and "SHARDED_CHAIN_OK" in res.stdout, (res.stdout[-1500:], res.stderr[-3000:])
+
+
 def test_shard_bounds_cover_everything():
     from cybayes_b200.synthetic import shard_bounds
     for n, g in ((1000000, 125000), (1000, 64), (5, 64), (129, 64)):
