@@ -86,7 +86,7 @@ def measured_peaks():
 
 
 _NVML_SAMPLER = r"""
-import sys, time
+import os, sys, time
 import pynvml as nv
 nv.nvmlInit()
 h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
@@ -94,7 +94,8 @@ mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
 reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
 out = open(sys.argv[2], "w")
 print("ready", mx, file=out, flush=True)
-while True:
+parent, t_max = os.getppid(), time.time() + 1800
+while os.getppid() == parent and time.time() < t_max:   # never outlives the bench process
     t = time.time()
     print(t, nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(reasons(h)), file=out, flush=True)
     time.sleep(0.005)
