@@ -312,7 +312,15 @@ def _slot_matrix(engine, tmats, edge_keys, getter=None, plan=None):
     n = len(edge_keys)
     S = engine.n_states
     n_host = sum(1 for t in tmats if not isinstance(t, PMatTable))
-    packed = np.empty((n_host, n * S * S), dtype=np.float64) if n_host else None
+    packed = None
+    if n_host:
+        # one packing buffer per engine, reused: upload_pmats has copied it into pinned staging when it returns, and a
+        # fresh 134 MB array per call (C5) would cost 32 000 page faults before a single matrix is packed
+        need = n_host * n * S * S
+        buf = getattr(engine, "_pack_buf", None)
+        if buf is None or buf.size < need:
+            buf = engine._pack_buf = np.empty(need, dtype=np.float64)
+        packed = buf[:need].reshape(n_host, n * S * S)
     host = []   # (column index, permutation or None) of the host-side categories, in the order of `packed`
     for t in tmats:
         if isinstance(t, PMatTable):
