@@ -2130,6 +2130,7 @@ extern "C" int cb_chain_create(cb_ctx* ctx, const cb_chain_backend* be, int n_ta
     ch.be = *be;
     ch.n_taxa = n_taxa; ch.S = n_states; ch.C = n_cats; ch.model = model; ch.binary = binary != 0; ch.root = root;
     ch.host_exp_max = host_exp_max;
+    if (const char* e = getenv("CYBAYES_CHAIN_LNL_FIRST")) ch.lnl_first = atoi(e) != 0 ? 1 : 0;   // default: automatic
     ch.param_ids.assign(param_ids, param_ids + n_params);
     ch.params_cdf.assign(params_cdf, params_cdf + n_params);
     ch.tree_cdf.assign(tree_cdf, tree_cdf + 2);

@@ -92,6 +92,12 @@ struct Chain {
   MT19937 py, np_;
   std::vector<int32_t> free_slots;
   int64_t n_moves[MV_COUNT] = {0}, n_accepts[MV_COUNT] = {0};
+  // Full-table proposals (pi / rates / alpha) on a large alignment: a rejected one needs no cache, and a pass that
+  // keeps none is cheaper (C4: 4.9 instead of 5.9 ms).  While such proposals are rarely accepted the chain asks for the
+  // likelihood only and repeats the pass with the cache on the rare acceptance (same operands, same bits -- checked).
+  // lnl_first: -1 = decide from the context and the acceptance count, 0 = never, 1 = always (CYBAYES_CHAIN_LNL_FIRST).
+  int lnl_first = -1;
+  int64_t full_props = 0, full_accepts = 0;
   std::string err;
   // scratch
   std::vector<int32_t> nodes, children, pslots, kid0, kid1, parent_of, index_of, order_nodes;
@@ -110,9 +116,11 @@ static int be_build(Chain* ch, int model, const double* pi, double beta, const d
   return cb_pmat_build(ch->ctx, model, pi, beta, gtr, count, slots, d, x);
 }
 static int be_eval(Chain* ch, int snap_in, int n_ops, const int32_t* nodes, const int32_t* children, const int32_t* pslots,
-                   const double* pi, int* snap_out, double* lnl) {
-  if (ch->be.eval) return ch->be.eval(ch->be.user, snap_in, n_ops, nodes, children, pslots, pi, CB_EVAL_WANT_SNAPSHOT, snap_out, lnl);
-  return cb_eval(ch->ctx, snap_in, n_ops, nodes, children, pslots, pi, CB_EVAL_WANT_SNAPSHOT, snap_out, lnl);
+                   const double* pi, int* snap_out, double* lnl, bool keep_cache = true) {
+  const int flags = keep_cache ? CB_EVAL_WANT_SNAPSHOT : 0;
+  *snap_out = -1;
+  if (ch->be.eval) return ch->be.eval(ch->be.user, snap_in, n_ops, nodes, children, pslots, pi, flags, snap_out, lnl);
+  return cb_eval(ch->ctx, snap_in, n_ops, nodes, children, pslots, pi, flags, snap_out, lnl);
 }
 static void be_release(Chain* ch, int snap) {
   if (snap < 0) return;
@@ -177,7 +185,8 @@ static inline void op_children(const std::vector<int32_t>& k0, const std::vector
 
 // Evaluate the op list of `todo` nodes (in plan order) on `tree`; snap_in < 0 = full evaluation.
 static int evaluate(Chain* ch, const std::vector<Edge>& tree, const std::vector<int32_t>& k0, const std::vector<int32_t>& k1,
-                    const std::vector<int32_t>& todo, int snap_in, const double* pi, int* snap_out, double* lnl) {
+                    const std::vector<int32_t>& todo, int snap_in, const double* pi, int* snap_out, double* lnl,
+                    bool keep_cache = true) {
   const int C = ch->C, n = (int)todo.size();
   ch->nodes.resize(n);
   ch->children.resize(2 * (size_t)n);
@@ -197,7 +206,19 @@ static int evaluate(Chain* ch, const std::vector<Edge>& tree, const std::vector<
       for (int q = 0; q < C; ++q) ch->pslots[(size_t)(2 * i + kx) * C + q] = e.slot[q];
     }
   }
-  return be_eval(ch, snap_in, n, ch->nodes.data(), ch->children.data(), ch->pslots.data(), pi, snap_out, lnl);
+  return be_eval(ch, snap_in, n, ch->nodes.data(), ch->children.data(), ch->pslots.data(), pi, snap_out, lnl, keep_cache);
+}
+
+// likelihood first, cache on acceptance?  Only where keeping the cache costs real bandwidth (a cache of 1 GB and more:
+// the reference datasets are latency-bound either way) and only while full-table proposals are accepted less than
+// one time in eight (the repeat costs a whole pass).  The decision depends on the chain's own history only, so the
+// ranks of a sharded chain take it alike.
+static bool lnl_first_now(const Chain* ch) {
+  if (ch->lnl_first >= 0) return ch->lnl_first != 0;
+  if (!ch->ctx) return false;
+  const double cache_bytes = (double)ch->ctx->P * ch->C * ch->S * 8.0 * (ch->n_taxa - 1);
+  if (cache_bytes < 1e9) return false;
+  return ch->full_props >= 8 && ch->full_accepts * 8 < ch->full_props;
 }
 
 // ---- P matrices (subst._queue) -----------------------------------------------------------------------------
@@ -480,8 +501,9 @@ static int run(Chain* ch, int64_t n_gens, int8_t* t_move, int8_t* t_acc, double*
       for (const Edge& e : prop)
         for (int k = 0; k < C; ++k) new_slots.push_back(e.slot[k]);
       plan_nodes(ch, k0, k1);
-      if (evaluate(ch, prop, k0, k1, ch->order_nodes, -1, pi_prop.data(), &prop_snap, &proposed)) return 1;
+      if (evaluate(ch, prop, k0, k1, ch->order_nodes, -1, pi_prop.data(), &prop_snap, &proposed, !lnl_first_now(ch))) return 1;
       full_tables = true;
+      ch->full_props++;
     }
 
     const double current = ch->lnl;
@@ -489,6 +511,14 @@ static int run(Chain* ch, int64_t n_gens, int8_t* t_move, int8_t* t_acc, double*
     ll_ratio += hr;
     const double log_u = log(ch->py.res53());
     const bool accepted = log_u <= ll_ratio;
+    if (accepted && full_tables) {
+      ch->full_accepts++;
+      if (prop_snap < 0) {  // the likelihood-only pass was accepted: the same pass again, this time keeping its cache
+        double again = 0.0;
+        if (evaluate(ch, prop, k0, k1, ch->order_nodes, -1, pi_prop.data(), &prop_snap, &again)) return 1;
+        if (again != proposed || prop_snap < 0) return chain_fail(ch, "native chain: the repeated full pass gave another likelihood");
+      }
+    }
     if (accepted) {
       if (move == MV_SCALE_EDGE || move == MV_NODE_SLIDER) {
         ch->tree[changed_edges[0]].t = prop[0].t;

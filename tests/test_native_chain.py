@@ -80,3 +80,32 @@ def test_gtr_on_binary_data_runs_with_the_degenerate_block_skipped(golden_cases,
     assert [x[:3] for x in a] == [x[:3] for x in b]
     np.testing.assert_allclose([x[3] for x in a], [x[3] for x in b], rtol=1e-12)
     assert open(str(tmp_path / "p.trees")).read() == open(str(tmp_path / "n.trees")).read()
+
+
+def test_likelihood_first_policy_keeps_the_trace(golden_cases, fake_backend, tmp_path, monkeypatch):
+    """Full-table proposals (pi / alpha) evaluated without a cache and repeated with one on acceptance
+    (CYBAYES_CHAIN_LNL_FIRST=1; automatic on large alignments once such proposals are rarely accepted): same trace
+    as the reference, one extra evaluation per accepted full-table proposal and no snapshot left behind."""
+    from cybayes_b200.fastchain import run_chain_native
+    case = golden_cases["narrow_F81"]
+    rows, meta = load_trace("narrow_F81")
+    n_gen = 400
+
+    def run(tag):
+        rec = []
+        res = run_chain_native(golden_io.data_path(case), "F81", n_gen, 1, "bin", str(tmp_path / tag), out=io.StringIO(),
+                               on_generation=lambda i, cur, prop, p, mv, acc, st: rec.append((i, cur, prop, p, mv, acc)))
+        eng = fake_backend.instances[-1]
+        return rec, res, eng.n_evals, len(eng.snaps)
+
+    rec0, res0, evals0, snaps0 = run("plain")
+    monkeypatch.setenv("CYBAYES_CHAIN_LNL_FIRST", "1")
+    from cybayes_b200 import likelihood
+    likelihood.reset_engines()
+    rec1, res1, evals1, snaps1 = run("first")
+    compare_trace(rec1, rows[:n_gen], meta, res1["initial_lnL"], 1e-11)
+    assert rec1 == rec0
+    accepted_full = sum(1 for (_, _, _, p, _, acc) in rec1 if acc and p in ("pi", "srates"))
+    assert accepted_full > 0 and evals1 == evals0 + accepted_full
+    assert snaps1 == snaps0
+    assert open(str(tmp_path / "plain.trees")).read() == open(str(tmp_path / "first.trees")).read()
